@@ -1,0 +1,781 @@
+// ecg_core.cuh -- one match-3 board, register resident, stepped by one thread.
+//
+// Restates (bit-exactly, see tests/) the reference hot path
+//   match3tile/boardFunctions.py : legal_actions :26-112, swap :115, get_matches :121-156,
+//                                  get_match_spawn_mask :159-169, shuffle :16-23
+//   match3tile/boardv2.py        : apply_action :43-207
+// on a bit-sliced board: 4 code bit-planes p[0..3] over the padded row-major bitboard of
+// ecg_bits.cuh.  Cell codes: 0 empty, 1..11 plain token of that type, 12 h_line, 13 v_line,
+// 14 bomb, 15 mega (specials are typeless in the reference: value & type_mask == 0).
+//
+// __host__ __device__ throughout: nvcc builds the sm_100a kernels from it, g++ builds the
+// test-only host simulator (tests/hostsim) that is fuzzed against the CPU oracle.
+#pragma once
+#include "ecg_bits.cuh"
+
+namespace ecg {
+
+enum : uint32_t {
+    ST_TERMINAL = 1,        // moves_left < 1: board returned unchanged (boardv2.py:44)
+    ST_STREAM_OVERFLOW = 2, // replay stream exhausted
+    ST_SHUFFLE_CAP = 4,     // shuffle loop capped (the reference would spin forever)
+    ST_BAD_ACTION = 8,      // action outside [0, action_space) (reference: KeyError, boardv2.py:48)
+    ST_NO_LEGAL = 16,       // random pick on an empty legal set (reference: ValueError)
+    ST_BAD_CELL = 32,       // pack: cell value outside the engine's closed code set
+    ST_CASCADE_CAP = 64,    // cascade loop capped (the reference has no cap; tiny type counts never settle)
+};
+constexpr int SHUFFLE_CAP = 64;
+constexpr int CASCADE_CAP = 1024;
+
+enum : int { K_HLINE = 0, K_VLINE = 1, K_BOMB = 2, K_MEGA = 3 };
+
+// ------------------------------------------------------------------ RNG sources
+
+// Philox4x32-10 (Salmon et al. SC'11).  One substream per (board, step):
+// u32 #k of the substream = philox(ctr = (k>>2, step, board_lo, board_hi), key)[k & 3].
+ECG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = l1;
+        c2 = n2;
+        c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// Throughput mode: bounded ints by multiply-high of one u32 (no rejection).
+struct PhiloxRng {
+    uint32_t k0, k1, b0, b1, step;
+    uint32_t pos;
+    uint32_t blk[4];
+    uint32_t blk_idx;
+    bool overflow;
+    ECG_HD void init(uint64_t key, uint64_t board, uint32_t step_) {
+        k0 = (uint32_t)key;
+        k1 = (uint32_t)(key >> 32);
+        b0 = (uint32_t)board;
+        b1 = (uint32_t)(board >> 32);
+        step = step_;
+        pos = 0;
+        blk_idx = 0xFFFFFFFFu;
+        blk[0] = blk[1] = blk[2] = blk[3] = 0u;
+        overflow = false;
+    }
+    ECG_HD void reseed() {} // counter-based: one substream per (board, step), never restarted
+    ECG_HD uint32_t u32() {
+        const uint32_t k = pos++;
+        const uint32_t b = k >> 2;
+        if (b != blk_idx) {
+            philox4x32_10(b, step, b0, b1, k0, k1, blk);
+            blk_idx = b;
+        }
+        const uint32_t j = k & 3u;
+        return j == 0 ? blk[0] : j == 1 ? blk[1] : j == 2 ? blk[2] : blk[3];
+    }
+    ECG_HD uint32_t below(uint32_t n) { return n <= 1u ? 0u : mulhi32(u32(), n); }
+};
+
+// The action pick of a Philox lockstep step: idx = mulhi(philox(ctr=(0xFFFFFFFF, step, board))[0], n)
+ECG_HD uint32_t philox_pick(uint64_t key, uint64_t board, uint32_t step, uint32_t n) {
+    uint32_t o[4];
+    philox4x32_10(0xFFFFFFFFu, step, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)key, (uint32_t)(key >> 32), o);
+    return n <= 1u ? 0u : mulhi32(o[0], n);
+}
+
+// Parity mode: replays the raw u32 output of numpy's legacy MT19937 (np.random.seed(cfg.seed)
+// restarts it at the top of every apply_action, boardv2.py:46, and in shuffle, boardFunctions.py:17)
+// with numpy's masked-rejection bounded integers (RandomState.randint / random_interval).
+struct ReplayRng {
+    const uint32_t *raw;
+    uint32_t len, pos;
+    bool overflow;
+    ECG_HD void init(const uint32_t *raw_, uint32_t len_, uint32_t pos_) {
+        raw = raw_;
+        len = len_;
+        pos = pos_;
+        overflow = false;
+    }
+    ECG_HD void reseed() { pos = 0; }
+    ECG_HD uint32_t u32() {
+        const uint32_t k = pos++;
+        if (k >= len) {
+            overflow = true;
+            return 0u;
+        }
+        return raw[k];
+    }
+    ECG_HD uint32_t below(uint32_t n) {
+        if (n <= 1u) return 0u;
+        const uint32_t rng = n - 1u;
+        uint32_t mask = rng;
+        mask |= mask >> 1;
+        mask |= mask >> 2;
+        mask |= mask >> 4;
+        mask |= mask >> 8;
+        mask |= mask >> 16;
+        for (;;) {
+            const uint32_t v = u32() & mask;
+            if (v <= rng || overflow) return v <= rng ? v : 0u;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ board
+
+template <class G>
+struct Board {
+    BB<G::W> p[4];
+};
+
+// Static per-shape parameters.  TPL = token planes that can differ between plain tokens
+// (3 when types <= 7, else 4); CLIP = np.clip(next_state, 0, 32) (boardv2.py:163) bites,
+// i.e. type_mask == 15: spawned bombs (48) and megas (64) become 32 == v_line.
+template <int R_, int C_, int TPL_, bool CLIP_>
+struct Shape {
+    using G = Geo<R_, C_>;
+    static constexpr int TPL = TPL_;
+    static constexpr bool CLIP = CLIP_;
+};
+
+template <class G>
+struct Derived { // views of a board used by match / legal logic
+    BB<G::W> spec; // special cells
+    BB<G::W> nz;   // cells holding a plain token
+    BB<G::W> q[4]; // token planes (zero on specials)
+};
+
+template <class SH>
+ECG_HD Derived<typename SH::G> derive(const Board<typename SH::G> &b) {
+    using G = typename SH::G;
+    Derived<G> d;
+    d.spec = b.p[3] & b.p[2];
+    d.nz = andn(b.p[0] | b.p[1] | b.p[2] | b.p[3], d.spec);
+#pragma unroll
+    for (int k = 0; k < 4; k++) d.q[k] = andn(b.p[k], d.spec);
+    return d;
+}
+
+// bit b: token(b) == token(b + K) and both are plain tokens
+template <class SH, int K>
+ECG_HD BB<SH::G::W> eq_at(const Derived<typename SH::G> &d) {
+    constexpr int W = SH::G::W;
+    BB<W> diff = d.q[0] ^ shr<K>(d.q[0]);
+#pragma unroll
+    for (int k = 1; k < SH::TPL; k++) diff |= d.q[k] ^ shr<K>(d.q[k]);
+    return andn(d.nz, diff);
+}
+
+template <class G>
+struct Matches {
+    BB<G::W> mask;       // cells cleared by get_matches
+    BB<G::W> sp;         // spawn cells (get_match_spawn_mask != 0)
+    BB<G::W> sk0, sk1;   // spawn kind bits
+    BB<G::W> A, D;       // eq-right / eq-down of the analysed board (reused by legal_mask)
+    bool found;
+};
+
+template <class SH>
+ECG_HD void add_spawn(Matches<typename SH::G> &m, const BB<SH::G::W> &cells, int kind) {
+    if (SH::CLIP && kind >= K_BOMB) kind = K_VLINE; // np.clip(.., 0, 32): 48 and 64 -> 32 == v_line
+    // a later group overwrites an earlier one at the same centre (boardFunctions.py:164-168)
+    m.sk0 = andn(m.sk0, cells);
+    m.sk1 = andn(m.sk1, cells);
+    m.sp |= cells;
+    if (kind & 1) m.sk0 |= cells;
+    if (kind & 2) m.sk1 |= cells;
+}
+
+template <class G>
+ECG_HD int run_right(const BB<G::W> &A, int b) { // cells in the A-chain starting at b (>= 1)
+    return 1 + ctz32(~extract32(A, b));
+}
+template <class G>
+ECG_HD int run_down(const BB<G::W> &D, int b) {
+    int n = 1;
+    while (testbit(D, b)) {
+        n++;
+        b += G::S;
+    }
+    return n;
+}
+
+// Straight-run spawns for runs of length >= 5 (mega tokens), rare.
+template <class SH>
+ECG_HD_NOINLINE void mega_spawns(Matches<typename SH::G> &m, BB<SH::G::W> L5h, BB<SH::G::W> L5v) {
+    using G = typename SH::G;
+    while (any(L5h)) {
+        const int b = pop_lowest(L5h);
+        const int n = run_right<G>(m.A, b);
+        add_spawn<SH>(m, onehot<G::W>(b + n / 2), K_MEGA); // sorted(group)[len // 2], boardFunctions.py:13
+    }
+    while (any(L5v)) {
+        const int b = pop_lowest(L5v);
+        const int n = run_down<G>(m.D, b);
+        add_spawn<SH>(m, onehot<G::W>(b + (n / 2) * G::S), K_MEGA);
+    }
+}
+
+// Origins that fire both a horizontal and a vertical run (L / T corner at the origin):
+// group = H cells + V cells with the origin listed twice -> never a line -> bomb.
+template <class SH>
+ECG_HD_NOINLINE void corner_spawns(Matches<typename SH::G> &m, BB<SH::G::W> K) {
+    using G = typename SH::G;
+    while (any(K)) {
+        const int b = pop_lowest(K);
+        const int hl = run_right<G>(m.A, b), vl = run_down<G>(m.D, b);
+        const int idx = (hl + vl) / 2; // >= 3
+        // sorted multiset: (r,c),(r,c),(r,c+1)..(r,c+hl-1),(r+1,c)..(r+vl-1,c)
+        const int centre = idx <= hl ? b + idx - 1 : b + (idx - hl) * G::S;
+        add_spawn<SH>(m, onehot<G::W>(centre), K_BOMB);
+    }
+}
+
+// General group bookkeeping when a horizontal run crosses a vertical run that started in
+// an earlier row (boardFunctions.py:126-131 merges the later match into the FIRST earlier
+// group sharing a cell, keeping duplicates).  Rare; kept out of line.
+template <class SH>
+ECG_HD_NOINLINE void merged_spawns(Matches<typename SH::G> &m, const BB<SH::G::W> &HO, const BB<SH::G::W> &VO,
+                                   const BB<SH::G::W> &VC) {
+    using G = typename SH::G;
+    constexpr int W = G::W, MAXM = G::R * G::C / 3 + 1;
+    // record: origin bit (9) | hlen (5) << 9 | vlen (5) << 14 | gid (8) << 19
+    uint32_t rec[MAXM];
+    int nm = 0;
+    BB<W> O = HO | VO;
+    while (any(O)) {
+        const int b = pop_lowest(O);
+        const int r = b / G::S, c = b - r * G::S;
+        const int hl = testbit(HO, b) ? run_right<G>(m.A, b) : 0;
+        const int vl = testbit(VO, b) ? run_down<G>(m.D, b) : 0;
+        int gid = nm;
+        for (int x = 1; x < hl; x++) { // crossing cells of the H part: covered by an earlier vertical run
+            if (!testbit(VC, b + x)) continue;
+            for (int j = 0; j < nm; j++) {
+                const int ob = rec[j] & 511, ovl = (rec[j] >> 14) & 31, og = (int)(rec[j] >> 19);
+                const int orow = ob / G::S, ocol = ob - orow * G::S;
+                if (ovl && ocol == c + x && orow < r && r <= orow + ovl - 1) gid = og < gid ? og : gid;
+            }
+        }
+        rec[nm++] = (uint32_t)b | ((uint32_t)hl << 9) | ((uint32_t)vl << 14) | ((uint32_t)gid << 19);
+    }
+    for (int g = 0; g < nm; g++) {
+        if ((int)(rec[g] >> 19) != g) continue; // not a group creator
+        BB<W> once = bb_zero<W>(), twice = bb_zero<W>(), thrice = bb_zero<W>();
+        int n = 0, members = 0, hl0 = 0, vl0 = 0;
+        for (int j = g; j < nm; j++) {
+            if ((int)(rec[j] >> 19) != g) continue;
+            const int b = rec[j] & 511, hl = (rec[j] >> 9) & 31, vl = (rec[j] >> 14) & 31;
+            if (members == 0) {
+                hl0 = hl;
+                vl0 = vl;
+            }
+            members++;
+            n += hl + vl;
+            for (int x = 0; x < hl; x++) {
+                const BB<W> cell = onehot<W>(b + x);
+                thrice |= twice & cell;
+                twice |= once & cell;
+                once |= cell;
+            }
+            for (int y = 0; y < vl; y++) {
+                const BB<W> cell = onehot<W>(b + y * G::S);
+                thrice |= twice & cell;
+                twice |= once & cell;
+                once |= cell;
+            }
+        }
+        if (n <= 3) continue; // boardFunctions.py:161
+        int kind;
+        if (members == 1 && vl0 == 0) kind = n > 4 ? K_MEGA : K_VLINE;      // one row   (:163-164)
+        else if (members == 1 && hl0 == 0) kind = n > 4 ? K_MEGA : K_HLINE; // one column (:165-166)
+        else kind = K_BOMB;                                                  // (:168)
+        // centre = sorted(group)[n // 2] with duplicates (:8-13)
+        int idx = n / 2, centre = 0;
+        BB<W> walk = once;
+        while (any(walk)) {
+            const int b = pop_lowest(walk);
+            const int mult = 1 + (testbit(twice, b) ? 1 : 0) + (testbit(thrice, b) ? 1 : 0);
+            if (idx < mult) {
+                centre = b;
+                break;
+            }
+            idx -= mult;
+        }
+        add_spawn<SH>(m, onehot<W>(centre), kind);
+    }
+}
+
+// Exact scan-order semantics of get_matches when horizontal and vertical runs intersect
+// (SURVEY.md 8a row A4): rows top to bottom, carrying vcov = cells of the row covered by
+// vertical runs started above.  Per maximal equal segment [s,e] (len >= 3) the first column
+// p in [s, e-2] not in vcov fires and marks [p, e]; vertical origins are the uncovered cells
+// not in (p, e] with two equal cells below.  Carry-propagation finds p and [p, e] for all
+// segments of a row at once.
+template <class SH>
+ECG_HD_NOINLINE void scan_order_matches(Matches<typename SH::G> &m, const BB<SH::G::W> &hs, const BB<SH::G::W> &vs) {
+    using G = typename SH::G;
+    constexpr int W = G::W;
+    constexpr uint32_t RM = (1u << G::C) - 1u;
+    BB<W> HF = bb_zero<W>(), HO = bb_zero<W>(), VO = bb_zero<W>(), VC = bb_zero<W>();
+    uint32_t vcov = 0;
+    for (int r = 0; r < G::R; r++) {
+        const int b0 = r * G::S;
+        const uint32_t hs_r = extract32(hs, b0) & RM, A_r = extract32(m.A, b0) & RM;
+        const uint32_t vs_r = extract32(vs, b0) & RM, D_r = extract32(m.D, b0) & RM;
+        const uint32_t cand = hs_r & ~vcov;
+        const uint32_t first = cand & ~(A_r + cand);
+        const uint32_t fill = (A_r + first) ^ A_r;
+        const uint32_t vorig = vs_r & ~vcov & ~(fill & ~first);
+        // deposit the row words (values < 2^16, shift < 32 within a 2-word window)
+        const int wi = b0 >> 5, s = b0 & 31;
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            if (i == wi) {
+                HF.w[i] |= fill << s;
+                HO.w[i] |= first << s;
+                VO.w[i] |= vorig << s;
+                VC.w[i] |= vcov << s;
+            }
+            if (i == wi + 1 && s) {
+                HF.w[i] |= fill >> (32 - s);
+                HO.w[i] |= first >> (32 - s);
+                VO.w[i] |= vorig >> (32 - s);
+                VC.w[i] |= vcov >> (32 - s);
+            }
+        }
+        vcov = (vcov | vorig) & D_r;
+    }
+    m.mask = HF | VO | VC;
+    if (any(HF & VC)) { // a fired horizontal run crosses an earlier vertical run: groups merge
+        merged_spawns<SH>(m, HO, VO, VC);
+        return;
+    }
+    // every match is its own group
+    const BB<W> K = HO & VO;
+    const BB<W> HOs = andn(HO, K), VOs = andn(VO, K);
+    const BB<W> L4h = HOs & shr<2>(m.A), L4v = VOs & shr<2 * G::S>(m.D);
+    const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * G::S>(m.D);
+    add_spawn<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);        // horizontal 4-run -> v_line (:164)
+    add_spawn<SH>(m, shl<2 * G::S>(andn(L4v, L5v)), K_HLINE); // vertical 4-run -> h_line (:166)
+    if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
+    if (any(K)) corner_spawns<SH>(m, K);
+}
+
+// get_matches + get_match_spawn_mask of the token board (boardFunctions.py:121-169).
+template <class SH>
+ECG_HD void find_matches(const Derived<typename SH::G> &d, Matches<typename SH::G> &m) {
+    using G = typename SH::G;
+    constexpr int W = G::W, S = G::S;
+    m.A = eq_at<SH, 1>(d);
+    m.D = eq_at<SH, S>(d);
+    m.sp = bb_zero<W>();
+    m.sk0 = bb_zero<W>();
+    m.sk1 = bb_zero<W>();
+    const BB<W> hs = m.A & shr<1>(m.A); // b, b+1, b+2 equal
+    const BB<W> vs = m.D & shr<S>(m.D);
+    m.found = any(hs | vs);
+    if (!m.found) {
+        m.mask = bb_zero<W>();
+        return;
+    }
+    const BB<W> H3 = hs | shl<1>(hs) | shl<2>(hs);
+    const BB<W> V3 = vs | shl<S>(vs) | shl<2 * S>(vs);
+    if (any(H3 & V3)) { // intersecting runs: the reference's result depends on scan order
+        scan_order_matches<SH>(m, hs, vs);
+        return;
+    }
+    // disjoint straight runs: every maximal run is one group
+    m.mask = H3 | V3;
+    const BB<W> L4h = andn(hs, shl<1>(m.A)) & shr<2>(m.A); // run starts with >= 4 cells
+    const BB<W> L4v = andn(vs, shl<S>(m.D)) & shr<2 * S>(m.D);
+    if (any(L4h | L4v)) {
+        const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
+        add_spawn<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
+        add_spawn<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
+        if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
+    }
+}
+
+// ------------------------------------------------------------------ legal mask
+
+// legal_actions (boardFunctions.py:26-112) as two swap bitboards: HL bit x = swap (x, x+1),
+// VL bit x = swap (x, x+S).  A swap is legal iff either token is 0 (special / empty, :100), or
+// the tokens differ (:103) and a moved token completes a run of three with two equal tokens
+// that are not its swap partner (:41-61, :74-94).  A/D must be eq-right/eq-down of this board.
+template <class SH>
+ECG_HD void legal_swaps(const Derived<typename SH::G> &d, const BB<SH::G::W> &A, const BB<SH::G::W> &D,
+                        BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    using G = typename SH::G;
+    constexpr int W = G::W, S = G::S;
+    const BB<W> A2 = eq_at<SH, 2>(d) & G::notlastcol(); // tok(b) == tok(b+2); col C-1 would wrap into the next row
+    const BB<W> D2 = eq_at<SH, 2 * S>(d);
+    const BB<W> F = eq_at<SH, S + 1>(d); // down-right diagonal
+    const BB<W> Gd = eq_at<SH, S - 1>(d); // down-left diagonal
+    const BB<W> Gup = shl<S - 1>(Gd);    // tok(x) == tok(x - S + 1)
+    const BB<W> Fup = shl<S>(F);         // tok(x + 1) == tok(x - S)
+    const BB<W> G1 = shr<1>(Gd);         // tok(x + 1) == tok(x + S)
+    const BB<W> F1 = shl<1>(F);          // tok(x - 1) == tok(x + S)
+    const BB<W> Aup2 = shl<2>(A);
+    const BB<W> Dup2 = shl<2 * S>(D);
+    // horizontal swap (x, x+1)
+    BB<W> h = (A2 & shr<2>(A))                 // x -> x+1 joins (x+2, x+3)
+              | (Gup & F)                       // x -> x+1 between (x+1-S) and (x+1+S)
+              | (Gup & shl<2 * S - 1>(D))       // x -> x+1 under (x+1-2S, x+1-S)
+              | (F & shr<S + 1>(D))             // x -> x+1 above (x+1+S, x+1+2S)
+              | (shl<1>(A2) & Aup2)             // x+1 -> x joins (x-2, x-1)
+              | (Fup & G1)                      // x+1 -> x between (x-S) and (x+S)
+              | (Fup & Dup2)                    // x+1 -> x under (x-2S, x-S)
+              | (G1 & shr<S>(D));               // x+1 -> x above (x+S, x+2S)
+    // vertical swap (x, x+S)
+    BB<W> v = (D2 & shr<2 * S>(D))             // x -> x+S joins (x+2S, x+3S)
+              | (Gd & F)                        // x -> x+S between (x+S-1) and (x+S+1)
+              | (Gd & shr<S - 2>(A))            // x -> x+S right of (x+S-2, x+S-1)
+              | (F & shr<S + 1>(A))             // x -> x+S left of (x+S+1, x+S+2)
+              | (shl<S>(D2) & Dup2)             // x+S -> x joins (x-2S, x-S)
+              | (F1 & G1)                       // x+S -> x between (x-1) and (x+1)
+              | (F1 & Aup2)                     // x+S -> x right of (x-2, x-1)
+              | (G1 & shr<1>(A));               // x+S -> x left of (x+1, x+2)
+    const BB<W> zt = andn(G::valid(), d.nz);   // token == 0
+    HL = (andn(h, A) | zt | shr<1>(zt)) & G::hvalid();
+    VL = (andn(v, D) | zt | shr<S>(zt)) & G::vvalid();
+}
+
+// swap bitboards -> action-ordered mask, action = r*(2C-1) + c (horizontal) | + (C-1) + c (vertical)
+// (boardConfig.py:45-69)
+template <class G>
+ECG_HD void swaps_to_actions(const BB<G::W> &HL, const BB<G::W> &VL, uint32_t out[G::AW]) {
+#pragma unroll
+    for (int i = 0; i < G::AW; i++) out[i] = 0u;
+#pragma unroll
+    for (int r = 0; r < G::R; r++) {
+        constexpr uint32_t HM = (1u << (G::C - 1)) - 1u, VM = (1u << G::C) - 1u;
+        const uint64_t row = (uint64_t)(extract32(HL, r * G::S) & HM) |
+                             ((uint64_t)(extract32(VL, r * G::S) & VM) << (G::C - 1));
+        const int pos = r * G::ROWA, wi = pos >> 5, s = pos & 31;
+        const uint64_t sh = row << s; // <= 31 + 31 bits
+#pragma unroll
+        for (int i = 0; i < G::AW; i++) {
+            if (i == wi) out[i] |= (uint32_t)sh;
+            if (i == wi + 1) out[i] |= (uint32_t)(sh >> 32);
+        }
+    }
+}
+
+template <class G>
+ECG_HD int mask_count(const uint32_t m[G::AW]) {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < G::AW; i++) n += popc32(m[i]);
+    return n;
+}
+// index of the k-th (0-based) set bit, ascending == legal_actions[k]
+template <class G>
+ECG_HD int mask_select(const uint32_t m[G::AW], int k) {
+    int base = 0;
+    uint32_t w = 0;
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < G::AW; i++) {
+        const int c = popc32(m[i]);
+        if (!done) {
+            if (k < c) {
+                w = m[i];
+                base = 32 * i;
+                done = true;
+            } else {
+                k -= c;
+            }
+        }
+    }
+    for (int j = 0; j < k; j++) w &= w - 1u;
+    return base + ctz32(w | 0x80000000u);
+}
+
+// ------------------------------------------------------------------ step
+
+template <class G>
+ECG_HD void decode_action(int a, int &b1, int &b2) { // boardConfig.py:45-59 (columns >= 4)
+    const int r = a / G::ROWA, k = a - r * G::ROWA;
+    if (k < G::C - 1) {
+        b1 = r * G::S + k;
+        b2 = b1 + 1;
+    } else {
+        b1 = r * G::S + (k - (G::C - 1));
+        b2 = b1 + G::S;
+    }
+}
+
+template <class G>
+ECG_HD int cell_code(const Board<G> &b, int bit) {
+    return (testbit(b.p[0], bit) ? 1 : 0) | (testbit(b.p[1], bit) ? 2 : 0) | (testbit(b.p[2], bit) ? 4 : 0) |
+           (testbit(b.p[3], bit) ? 8 : 0);
+}
+template <class G>
+ECG_HD void set_code(Board<G> &b, int bit, int code) { // cell must be empty
+    const int wi = bit >> 5;
+    const uint32_t m = 1u << (bit & 31);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t mk = ((code >> k) & 1) ? m : 0u;
+#pragma unroll
+        for (int i = 0; i < G::W; i++) b.p[k].w[i] |= (i == wi) ? mk : 0u;
+    }
+}
+
+// effects of every special token on the board (boardv2.py:141-154): all of them fire in every
+// cascade iteration because a typeless special always has token_board == 0.
+template <class SH>
+ECG_HD_NOINLINE BB<SH::G::W> trigger_specials(const Board<typename SH::G> &bd, BB<SH::G::W> spec) {
+    using G = typename SH::G;
+    BB<G::W> z = bb_zero<G::W>();
+    while (any(spec)) {
+        const int b = pop_lowest(spec);
+        const int i = b / G::S, j = b - i * G::S;
+        const int kind = (testbit(bd.p[0], b) ? 1 : 0) | (testbit(bd.p[1], b) ? 2 : 0);
+        if (kind == K_HLINE) z |= G::rows(i, i + 1);
+        else if (kind == K_VLINE) z |= G::cols(j, j + 1);
+        else if (kind == K_BOMB && i > 0 && j > 0) // token_board[j-1:j+1, i-1:i+1] (transposed; a negative start empties the slice)
+            z |= G::rows(j - 1, j + 1) & G::cols(i - 1, i + 1);
+    }
+    return z;
+}
+
+// gravity (boardv2.py:166-173): every column keeps its non-empty cells, in order, at the bottom
+template <class G>
+ECG_HD void gravity(Board<G> &b) {
+    constexpr int W = G::W, S = G::S;
+    for (;;) {
+        const BB<W> occ = b.p[0] | b.p[1] | b.p[2] | b.p[3];
+        const BB<W> holes = andn(G::valid(), occ);
+        BB<W> u = shr<S>(holes); // a hole somewhere below in the column
+        u |= shr<S>(u);
+        u |= shr<2 * S>(u);
+        if (G::R > 4) u |= shr<4 * S>(u);
+        if (G::R > 8) u |= shr<8 * S>(u);
+        const BB<W> f = occ & u;
+        if (!any(f)) return;
+#pragma unroll
+        for (int k = 0; k < 4; k++) b.p[k] = andn(b.p[k], f) | shl<S>(b.p[k] & f);
+    }
+}
+
+// refill (boardv2.py:172-173): columns left to right, first draw = topmost hole
+template <class G, class RNG>
+ECG_HD void refill(Board<G> &b, RNG &rng, uint32_t types) {
+    const BB<G::W> holes = andn(G::valid(), b.p[0] | b.p[1] | b.p[2] | b.p[3]);
+    uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
+    while (cols) {
+        int bit = ctz32(cols);
+        cols &= cols - 1u;
+        do {
+            set_code(b, bit, 1 + (int)rng.below(types));
+            bit += G::S;
+        } while (bit < G::NB && testbit(holes, bit));
+    }
+}
+
+// boardFunctions.shuffle (:16-23): reseed, permute ROWS (numpy legacy Fisher-Yates), then cells
+// that held a special before the shuffle get their old value back.
+template <class SH, class RNG>
+ECG_HD_NOINLINE void shuffle_rows(Board<typename SH::G> &b, RNG &rng) {
+    using G = typename SH::G;
+    constexpr int W = G::W;
+    constexpr uint32_t RM = (1u << G::C) - 1u;
+    rng.reseed();
+    const Board<G> old = b;
+    const BB<W> old_spec = old.p[3] & old.p[2];
+    uint32_t rows[4][G::R];
+    for (int k = 0; k < 4; k++)
+        for (int r = 0; r < G::R; r++) rows[k][r] = extract32(b.p[k], r * G::S) & RM;
+    for (int i = G::R - 1; i >= 1; i--) {
+        const int j = (int)rng.below((uint32_t)i + 1u);
+        for (int k = 0; k < 4; k++) {
+            const uint32_t t = rows[k][j];
+            rows[k][j] = rows[k][i];
+            rows[k][i] = t;
+        }
+    }
+    for (int k = 0; k < 4; k++) {
+        BB<W> p = bb_zero<W>();
+        for (int r = 0; r < G::R; r++) {
+            const int b0 = r * G::S, wi = b0 >> 5, s = b0 & 31;
+            for (int i = 0; i < W; i++) {
+                if (i == wi) p.w[i] |= rows[k][r] << s;
+                if (i == wi + 1 && s) p.w[i] |= rows[k][r] >> (32 - s);
+            }
+        }
+        b.p[k] = andn(p, old_spec) | (old.p[k] & old_spec);
+    }
+}
+
+struct StepOut {
+    int reward;       // points of this step (boardv2.py:157-158 summed over the cascade)
+    int cascades;     // iterations of the cascade loop (:138), >= 1
+    uint32_t status;  // ST_* bits
+};
+
+// BoardV2.apply_action (boardv2.py:43-207) minus the terminal test.  On return `bd` is the next
+// board, `HL`/`VL` its legal swaps (the reference computes legal_actions on the final board too,
+// :188, to decide about shuffling).
+template <class SH, class RNG>
+ECG_HD void step_board(Board<typename SH::G> &bd, int action, uint32_t types, RNG &rng, StepOut &out,
+                       BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    using G = typename SH::G;
+    constexpr int W = G::W;
+    out.reward = 0;
+    out.cascades = 0;
+    out.status = 0;
+    rng.reseed(); // :46
+    int b1, b2;
+    decode_action<G>(action, b1, b2); // source, target (:48)
+    { // swap (:51)
+        const BB<W> m1 = onehot<W>(b1), m2 = onehot<W>(b2), both = m1 | m2;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool x = any(bd.p[k] & m1), y = any(bd.p[k] & m2);
+            if (x != y) bd.p[k] = bd.p[k] ^ both;
+        }
+    }
+    Derived<G> d = derive<SH>(bd);
+    Matches<G> m;
+    BB<W> cleared; // plain cells whose token_board entry was zeroed
+    const int c1 = cell_code<G>(bd, b1), c2 = cell_code<G>(bd, b2);
+    const int s1 = c1 >= 12 ? c1 - 11 : 0, s2 = c2 >= 12 ? c2 - 11 : 0; // 0 none, 1 h, 2 v, 3 bomb, 4 mega
+    bool matched = false;
+    if (s1 | s2) {
+        const int tr = b2 / G::S, tc = b2 - tr * G::S; // target (:112-132 are relative to the target cell)
+        const int lo = s1 < s2 ? s1 : s2, hi = s1 < s2 ? s2 : s1;
+        m.sp = bb_zero<W>();
+        m.sk0 = bb_zero<W>();
+        m.sk1 = bb_zero<W>();
+        cleared = bb_zero<W>();
+        if (hi == 4) { // a mega token is involved
+            if (lo == 4) cleared = G::valid(); // :81-82
+            // mega + bomb / line / plain (:84-103): token = max(token1, token2) is the mega value itself,
+            // never present in token_board -> no cell changes and get_matches is skipped
+        } else if (lo == 3 && hi == 3) { // bomb + bomb (:112-116)
+            cleared = G::rows(tr - 2, tr + 2) & G::cols(tc - 2, tc + 2);
+        } else if (hi == 3 && lo >= 1) { // bomb + line (:123-125)
+            cleared = G::cols(tc - 2, tc + 2) | G::rows(tr - 2, tr + 2);
+        } else if (lo == 1 && hi == 2) { // h_line + v_line (:130-132): ROW slices [:tc] and [tr:]
+            cleared = G::rows(0, tc) | G::rows(tr, G::R);
+        } else { // one special + plain, or two equal lines (:134-136)
+            matched = true;
+        }
+    } else {
+        matched = true;
+    }
+    if (matched) {
+        find_matches<SH>(d, m);
+        cleared = m.mask;
+    }
+    for (;;) { // :138
+        out.cascades++;
+        BB<W> z = cleared | d.spec | andn(G::valid(), d.nz | d.spec); // token_board == 0
+        if (any(d.spec)) z |= trigger_specials<SH>(bd, d.spec);
+        { // points (:58-65, :157-158)
+            const BB<W> k1 = bd.p[1] & d.spec, k0 = bd.p[0] & d.spec;
+            out.reward += 2 * popcount(andn(z, d.spec)) + 25 * popcount(andn(d.spec, k1)) +
+                          50 * popcount(andn(k1, k0)) + 250 * popcount(k1 & k0);
+        }
+        // :161-163 clear, add spawns (always onto cleared cells), clip
+#pragma unroll
+        for (int k = 0; k < 4; k++) bd.p[k] = andn(bd.p[k], z);
+        bd.p[3] |= m.sp;
+        bd.p[2] |= m.sp;
+        bd.p[0] |= m.sk0;
+        bd.p[1] |= m.sk1;
+        gravity<G>(bd);          // :166-170
+        refill<G>(bd, rng, types); // :172-173
+        d = derive<SH>(bd);
+        find_matches<SH>(d, m);  // :181
+        if (!m.found) {
+            legal_swaps<SH>(d, m.A, m.D, HL, VL);
+            int shuffles = 0;
+            while (!m.found && !any(HL | VL)) { // :188-194
+                if (shuffles++ >= SHUFFLE_CAP) {
+                    out.status |= ST_SHUFFLE_CAP;
+                    break;
+                }
+                shuffle_rows<SH>(bd, rng);
+                d = derive<SH>(bd);
+                find_matches<SH>(d, m);
+                if (!m.found) legal_swaps<SH>(d, m.A, m.D, HL, VL);
+            }
+            if (!m.found) break; // :195
+        }
+        cleared = m.mask; // :199
+        if (rng.overflow || out.cascades >= CASCADE_CAP) {
+            if (!rng.overflow) out.status |= ST_CASCADE_CAP;
+            legal_swaps<SH>(d, m.A, m.D, HL, VL);
+            break;
+        }
+    }
+    if (rng.overflow) out.status |= ST_STREAM_OVERFLOW;
+}
+
+// BoardV2.__init__ (boardv2.py:20-27): draw a board, redraw matched cells until clean.
+template <class SH, class RNG>
+ECG_HD void init_board(Board<typename SH::G> &bd, uint32_t types, RNG &rng) {
+    using G = typename SH::G;
+    rng.reseed();
+#pragma unroll
+    for (int k = 0; k < 4; k++) bd.p[k] = bb_zero<G::W>();
+    for (int r = 0; r < G::R; r++)
+        for (int c = 0; c < G::C; c++) set_code(bd, r * G::S + c, 1 + (int)rng.below(types));
+    Matches<G> m;
+    for (int guard = 0; guard < 100000; guard++) {
+        Derived<G> d = derive<SH>(bd);
+        find_matches<SH>(d, m);
+        if (!m.found || rng.overflow) break;
+        // a full board of fresh draws is consumed every round; only masked cells take theirs (:25-26)
+        Board<G> fresh;
+#pragma unroll
+        for (int k = 0; k < 4; k++) fresh.p[k] = bb_zero<G::W>();
+        for (int r = 0; r < G::R; r++)
+            for (int c = 0; c < G::C; c++) set_code(fresh, r * G::S + c, 1 + (int)rng.below(types));
+#pragma unroll
+        for (int k = 0; k < 4; k++) bd.p[k] = andn(bd.p[k], m.mask) | (fresh.p[k] & m.mask);
+    }
+}
+
+// ------------------------------------------------------------------ cell codec
+
+struct CellCodec { // boardConfig.py:29-43
+    int type_mask, h_line, v_line, bomb, mega;
+};
+ECG_HD CellCodec make_codec(int types) {
+    int bits = 0;
+    while ((1 << bits) < types + 1) bits++;
+    CellCodec c;
+    c.type_mask = (1 << bits) - 1;
+    c.h_line = c.type_mask + 1;
+    c.v_line = 2 * c.h_line;
+    c.bomb = (1 << (bits + 1)) + 1 + c.type_mask;
+    c.mega = c.type_mask + c.bomb + 1;
+    return c;
+}
+ECG_HD int encode_cell(const CellCodec &c, long long v) { // -> code or -1
+    if (v == 0) return 0;
+    if (v > 0 && v <= c.type_mask && v <= 11) return (int)v;
+    if (v == c.h_line) return 12;
+    if (v == c.v_line) return 13;
+    if (v == c.bomb) return 14;
+    if (v == c.mega) return 15;
+    return -1;
+}
+ECG_HD int decode_cell(const CellCodec &c, int code) {
+    return code < 12 ? code : code == 12 ? c.h_line : code == 13 ? c.v_line : code == 14 ? c.bomb : c.mega;
+}
+
+} // namespace ecg

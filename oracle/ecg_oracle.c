@@ -658,6 +658,10 @@ int ecgo_apply_action(const ecgo_cfg *cfg, ecgo_rng *rng, const int64_t *in, int
             get_matches(H, W, token_board, zeros_mask, &g);
         }
         if (g.n_groups == 0) break; /* :195 */
+        if (cascades >= ECGO_CASCADE_CAP) { /* the reference has no cap (tiny type counts cascade ~forever) */
+            status |= ECGO_ST_CASCADE_CAP;
+            break;
+        }
         for (int i = 0; i < N; i++)
             if (zeros_mask[i]) token_board[i] = 0; /* :199 */
         get_match_spawn_mask(cfg, &g, token_spawn); /* :202 */

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libecg_oracle.so")
 
-ST_TERMINAL, ST_STREAM_OVERFLOW, ST_SHUFFLE_CAP, ST_BAD_ACTION, ST_NO_LEGAL = 1, 2, 4, 8, 16
+ST_TERMINAL, ST_STREAM_OVERFLOW, ST_SHUFFLE_CAP, ST_BAD_ACTION, ST_NO_LEGAL, ST_BAD_CELL, ST_CASCADE_CAP = 1, 2, 4, 8, 16, 32, 64
 
 
 class Cfg(C.Structure):

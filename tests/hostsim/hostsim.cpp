@@ -1,0 +1,193 @@
+// hostsim.cpp -- TEST-ONLY host build of the kernel core (element-crush-gym_b200/csrc/ecg_core.cuh).
+// g++ compiles the exact __host__ __device__ board logic that nvcc puts into the sm_100a kernels, so
+// the bitboard algorithm can be fuzzed against the CPU oracle without a GPU.  Not part of the product:
+// nothing under element-crush-gym_b200/ loads this library.
+#include <cstdint>
+#include <cstring>
+
+#include "../../element-crush-gym_b200/csrc/ecg_core.cuh"
+
+using namespace ecg;
+
+template <class SH>
+static uint32_t pack_board(const CellCodec &cc, const int64_t *cells, Board<typename SH::G> &b) {
+    using G = typename SH::G;
+    uint32_t st = 0;
+    for (int k = 0; k < 4; k++) b.p[k] = bb_zero<G::W>();
+    for (int r = 0; r < G::R; r++)
+        for (int c = 0; c < G::C; c++) {
+            int code = encode_cell(cc, cells[r * G::C + c]);
+            if (code < 0) {
+                st |= ST_BAD_CELL;
+                code = 0;
+            }
+            set_code(b, r * G::S + c, code);
+        }
+    return st;
+}
+
+template <class SH>
+static void unpack_board(const CellCodec &cc, const Board<typename SH::G> &b, int64_t *cells) {
+    using G = typename SH::G;
+    for (int r = 0; r < G::R; r++)
+        for (int c = 0; c < G::C; c++) cells[r * G::C + c] = decode_cell(cc, cell_code<G>(b, r * G::S + c));
+}
+
+template <class SH>
+static void legal_bytes(const BB<SH::G::W> &HL, const BB<SH::G::W> &VL, uint8_t *out) {
+    using G = typename SH::G;
+    uint32_t m[G::AW];
+    swaps_to_actions<G>(HL, VL, m);
+    for (int a = 0; a < G::A; a++) out[a] = (m[a >> 5] >> (a & 31)) & 1u;
+}
+
+struct StepArgs {
+    int types, mode;
+    const uint32_t *raw;
+    int64_t raw_stride, raw_len;
+    uint64_t key, board0;
+    uint32_t step_ctr;
+    const int64_t *in;
+    const int32_t *actions, *moves_left;
+    int64_t *out, *reward;
+    int32_t *cascades;
+    uint8_t *status, *legal;
+    int64_t n;
+};
+
+template <class SH>
+static void step_t(const StepArgs &a) {
+    using G = typename SH::G;
+    const CellCodec cc = make_codec(a.types);
+    const int N = G::R * G::C;
+    for (int64_t i = 0; i < a.n; i++) {
+        Board<G> b;
+        uint32_t st = pack_board<SH>(cc, a.in + i * N, b);
+        StepOut so = {0, 0, 0};
+        BB<G::W> HL, VL;
+        const bool terminal = a.moves_left && a.moves_left[i] < 1;
+        const bool bad = a.actions[i] < 0 || a.actions[i] >= G::A;
+        if (terminal || bad) {
+            so.status = terminal ? ST_TERMINAL : ST_BAD_ACTION;
+            Derived<G> d = derive<SH>(b);
+            legal_swaps<SH>(d, eq_at<SH, 1>(d), eq_at<SH, G::S>(d), HL, VL);
+        } else if (a.mode == 2) {
+            PhiloxRng rng;
+            rng.init(a.key, a.board0 + (uint64_t)i, a.step_ctr);
+            step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+        } else {
+            ReplayRng rng;
+            rng.init(a.raw + i * a.raw_stride, (uint32_t)a.raw_len, 0);
+            step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+        }
+        unpack_board<SH>(cc, b, a.out + i * N);
+        if (a.reward) a.reward[i] = so.reward;
+        if (a.cascades) a.cascades[i] = so.cascades;
+        if (a.status) a.status[i] = (uint8_t)(so.status | st);
+        if (a.legal) legal_bytes<SH>(HL, VL, a.legal + i * G::A);
+    }
+}
+
+template <class SH>
+static void legal_t(int types, const int64_t *boards, uint8_t *legal, int64_t n) {
+    using G = typename SH::G;
+    const CellCodec cc = make_codec(types);
+    for (int64_t i = 0; i < n; i++) {
+        Board<G> b;
+        pack_board<SH>(cc, boards + i * G::R * G::C, b);
+        Derived<G> d = derive<SH>(b);
+        BB<G::W> HL, VL;
+        legal_swaps<SH>(d, eq_at<SH, 1>(d), eq_at<SH, G::S>(d), HL, VL);
+        legal_bytes<SH>(HL, VL, legal + i * G::A);
+    }
+}
+
+// get_matches + get_match_spawn_mask on the token board of `boards` (plain tokens only matter)
+template <class SH>
+static void matches_t(int types, const int64_t *boards, uint8_t *mask, int32_t *spawn, int64_t n) {
+    using G = typename SH::G;
+    const CellCodec cc = make_codec(types);
+    const int kinds[4] = {cc.h_line, cc.v_line, cc.bomb, cc.mega};
+    for (int64_t i = 0; i < n; i++) {
+        Board<G> b;
+        pack_board<SH>(cc, boards + i * G::R * G::C, b);
+        Derived<G> d = derive<SH>(b);
+        Matches<G> m;
+        find_matches<SH>(d, m);
+        for (int r = 0; r < G::R; r++)
+            for (int c = 0; c < G::C; c++) {
+                const int bit = r * G::S + c;
+                mask[i * G::R * G::C + r * G::C + c] = m.found && testbit(m.mask, bit);
+                int v = 0;
+                if (m.found && testbit(m.sp, bit)) v = kinds[(testbit(m.sk0, bit) ? 1 : 0) | (testbit(m.sk1, bit) ? 2 : 0)];
+                spawn[i * G::R * G::C + r * G::C + c] = v;
+            }
+    }
+}
+
+template <class SH>
+static void init_t(int types, const uint32_t *raw, int64_t raw_stride, int64_t raw_len, uint64_t key,
+                   uint64_t board0, int mode, int64_t *out, uint8_t *status, int64_t n) {
+    using G = typename SH::G;
+    const CellCodec cc = make_codec(types);
+    for (int64_t i = 0; i < n; i++) {
+        Board<G> b;
+        bool ovf;
+        if (mode == 2) {
+            PhiloxRng rng;
+            rng.init(key, board0 + (uint64_t)i, 0xFFFFFFFFu);
+            init_board<SH>(b, (uint32_t)types, rng);
+            ovf = false;
+        } else {
+            ReplayRng rng;
+            rng.init(raw + i * raw_stride, (uint32_t)raw_len, 0);
+            init_board<SH>(b, (uint32_t)types, rng);
+            ovf = rng.overflow;
+        }
+        unpack_board<SH>(cc, b, out + i * G::R * G::C);
+        if (status) status[i] = ovf ? ST_STREAM_OVERFLOW : 0;
+    }
+}
+
+#define DISPATCH(rows, types, CALL)                                                      \
+    do {                                                                                 \
+        const bool wide = (types) >= 8;                                                  \
+        switch (rows) {                                                                  \
+        case 5: if (wide) { using SH = Shape<5, 5, 4, true>; CALL; } else { using SH = Shape<5, 5, 3, false>; CALL; } return 0;     \
+        case 6: if (wide) { using SH = Shape<6, 6, 4, true>; CALL; } else { using SH = Shape<6, 6, 3, false>; CALL; } return 0;     \
+        case 7: if (wide) { using SH = Shape<7, 7, 4, true>; CALL; } else { using SH = Shape<7, 7, 3, false>; CALL; } return 0;     \
+        case 9: if (wide) { using SH = Shape<9, 9, 4, true>; CALL; } else { using SH = Shape<9, 9, 3, false>; CALL; } return 0;     \
+        case 12: if (wide) { using SH = Shape<12, 12, 4, true>; CALL; } else { using SH = Shape<12, 12, 3, false>; CALL; } return 0; \
+        case 16: if (wide) { using SH = Shape<16, 16, 4, true>; CALL; } else { using SH = Shape<16, 16, 3, false>; CALL; } return 0; \
+        default: return -1;                                                              \
+        }                                                                                \
+    } while (0)
+
+extern "C" {
+
+int hs_step(int rows, int cols, int types, int mode, const uint32_t *raw, int64_t raw_stride, int64_t raw_len,
+            uint64_t key, uint64_t board0, uint32_t step_ctr, const int64_t *in, const int32_t *actions,
+            const int32_t *moves_left, int64_t *out, int64_t *reward, int32_t *cascades, uint8_t *status,
+            uint8_t *legal, int64_t n) {
+    if (rows != cols || types < 1 || types > 11) return -1;
+    StepArgs a = {types, mode, raw, raw_stride, raw_len, key, board0, step_ctr, in, actions, moves_left,
+                  out, reward, cascades, status, legal, n};
+    DISPATCH(rows, types, step_t<SH>(a));
+}
+
+int hs_legal(int rows, int cols, int types, const int64_t *boards, uint8_t *legal, int64_t n) {
+    if (rows != cols || types < 1 || types > 11) return -1;
+    DISPATCH(rows, types, legal_t<SH>(types, boards, legal, n));
+}
+
+int hs_matches(int rows, int cols, int types, const int64_t *boards, uint8_t *mask, int32_t *spawn, int64_t n) {
+    if (rows != cols || types < 1 || types > 11) return -1;
+    DISPATCH(rows, types, matches_t<SH>(types, boards, mask, spawn, n));
+}
+
+int hs_init(int rows, int cols, int types, int mode, const uint32_t *raw, int64_t raw_stride, int64_t raw_len,
+            uint64_t key, uint64_t board0, int64_t *out, uint8_t *status, int64_t n) {
+    if (rows != cols || types < 1 || types > 11) return -1;
+    DISPATCH(rows, types, init_t<SH>(types, raw, raw_stride, raw_len, key, board0, mode, out, status, n));
+}
+}
