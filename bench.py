@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- 9x9x6 env-steps/sec (cascades included) of the batched stepping engine.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload = BASELINE.json configs[2] (SURVEY.md 8d "config 3"): 2^24 lockstep 9x9x6 boards PER GPU (weak
+scaling; Philox keyed by global board index, so results do not depend on N), each step = pick a uniformly
+random legal action from the previous legal mask -> swap -> full cascade -> reward/done/won -> new legal mask.
+One step of all boards is ONE launch of the step kernel.  Inputs are resident in HBM (1.1 GB of boards + masks,
+far larger than the 126 MB L2, so no explicit L2 flush is needed between steps).
+
+The JSON line also carries
+  e2e          the same metric through the public host-buffer API (HostStepper): per step the actions are
+               fetched to pinned host memory (board.random_action()), copied back H2D, and obs/reward/flags are
+               read D2H, all inside the timed region;
+  roofline     algorithmic bytes per launch (117 B per env-step) / average step-kernel duration;
+  cpu_baseline the CPU oracle port (oracle/, test infrastructure) timed on this box's host cores, rank 0, N=1.
+--impl reference times that CPU port on all host threads as the reference arm (the reference itself is pure
+Python with no compiled sources and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "9x9x6 env-steps/sec (cascades incl.)"
+UNIT = "env-steps/s"
+KEY = 0x9E3779B97F4A7C15
+SHAPE = (9, 9, 6)
+BYTES_PER_STEP = 117  # 2*ceil(81/2) + 17 + ceil(144/8), SURVEY.md 8d
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(boards_per_gpu, n_gpus):
+    return {
+        "workload": "configs[2]: lockstep 9x9x6 boards, random legal action from the previous mask + step + "
+                    "cascade + reward/done/won + legal-swap mask every step, Philox4x32-10 refill",
+        "boards_per_gpu": boards_per_gpu, "boards_total": boards_per_gpu * n_gpus,
+        "rows": 9, "cols": 9, "types": 6, "refill": "philox4x32-10", "legal_mask_each_step": True,
+        "l2": "inputs (boards+masks, %.2f GB per GPU) exceed the 126 MB L2; no flush" %
+              (boards_per_gpu * (48 + 20) / 1e9),
+        "parallelism": f"{n_gpus} x independent shards by global board index, no collective in the step path",
+    }
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu capture, if any"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU port (oracle) legs
+
+def cpu_port_rate(target_seconds, threads=None):
+    """env-steps/s of the oracle port on the host: lockstep Philox steps over a bounded sample of boards."""
+    import numpy as np
+    from oracle.oracle import Oracle
+    o = Oracle(*SHAPE)
+    if threads:
+        Oracle.set_threads(threads)
+    cores = Oracle.max_threads()
+    n0 = 4096 * max(1, cores // 4)
+    boards = np.stack([o.init_board(o.rng_philox(KEY, i, 0xFFFFFFFF)) for i in range(512)])
+    boards = np.tile(boards, (n0 // 512 + 1, 1, 1))[:n0].copy()
+    t = time.perf_counter()
+    o.philox_episode_batch(boards, KEY, 0, 4, step0=0, inplace=True)
+    rate = n0 * 4 / (time.perf_counter() - t)
+    moves = 20
+    n = int(min(max(rate * target_seconds / moves, 1024), 1 << 22)) // 512 * 512
+    boards = np.tile(boards[:512], (n // 512, 1, 1)).copy()
+    t = time.perf_counter()
+    _, _, steps = o.philox_episode_batch(boards, KEY, 0, moves, step0=4, inplace=True)
+    dt = time.perf_counter() - t
+    return {"value": float(steps.sum() / dt), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} boards x {moves} lockstep steps (pick + step + cascade + legal mask), "
+                      f"{dt:.1f} s on {cores} host threads; C oracle port of the reference's Python/NumPy path"}
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path (oracle port; the reference is Python-only) on all
+    host threads; each step = one lockstep step of a bounded sample of the workload's boards."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle.oracle import Oracle
+    o = Oracle(*SHAPE)
+    cores = Oracle.max_threads()
+    n = 2048 * cores
+    base = np.stack([o.init_board(o.rng_philox(KEY, i, 0xFFFFFFFF)) for i in range(512)])
+    boards = np.tile(base, (n // 512 + 1, 1, 1))[:n].copy()
+    t = time.perf_counter()
+    o.philox_episode_batch(boards, KEY, 0, 2, step0=0, inplace=True)
+    rate = n * 2 / (time.perf_counter() - t)
+    budget = 120.0 / max(args.steps + args.warmup, 1)  # whole run within a few minutes
+    per_step = min(0.5, budget)
+    n = int(min(max(rate * per_step, 512), args.boards)) // 512 * 512
+    boards = np.tile(base, (n // 512, 1, 1)).copy()
+    for w in range(args.warmup):
+        o.philox_episode_batch(boards, KEY, 0, 1, step0=w, inplace=True)
+    t = time.perf_counter()
+    done = 0
+    for k in range(args.steps):
+        _, _, st = o.philox_episode_batch(boards, KEY, 0, 1, step0=args.warmup + k, inplace=True)
+        done += int(st.sum())
+    dt = time.perf_counter() - t
+    value = done / dt
+    cfg = workload(args.boards, args.gpus)
+    sample = f"{n} of the {args.boards} boards per step, {cores} host threads, C oracle port (reference is pure Python)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------ our arm
+
+def run_ours(args):
+    import torch
+    E = importlib.import_module("element-crush-gym_b200")
+    rank, world, local = E.dist.init_from_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    import torch.distributed as tdist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = args.boards
+    L = E._native.lib()
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    # episodes long enough that no board turns terminal inside the run (num_moves is a free env parameter)
+    env = E.BatchedMatch3Env(n, 9, 9, 6, num_moves=1 << 30, env_goal=500, seed=KEY, device=dev, refill="philox",
+                             board0=rank * n)
+    b = env.board
+    b.packed_mask()
+    for _ in range(args.warmup):
+        b.apply_action(None)
+    torch.cuda.synchronize(dev)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = L.ecg_launch_count()
+    torch.cuda.synchronize(dev)
+    ev[0].record()
+    for k in range(args.steps):
+        b.apply_action(None)  # ONE step-kernel launch: pick + swap + cascade + reward/flags + new mask
+        ev[k + 1].record()
+    torch.cuda.synchronize(dev)
+    launches = L.ecg_launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = ev[0].elapsed_time(ev[-1])
+    per_launch = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    ms_max = max_over_ranks(ms)
+    value = world * n * args.steps / (ms_max * 1e-3)
+    # health of the run: every board advanced every step
+    stuck = int(((b.status & E.ST_NO_LEGAL) != 0).sum().item())
+    bad = int(((b.status & ~E.ST_NO_LEGAL) != 0).sum().item())
+    stats = E.dist.stats_dict(E.dist.reduce_stats(b.episode_stats()))
+    mean_casc = float(b.cascades.float().mean().item())
+
+    # ---- e2e through the host-buffer API
+    e2e = None
+    if not args.no_e2e:
+        hs = E.HostStepper(env, chunks=8)
+        for _ in range(2):
+            hs.step(hs.random_action())
+        torch.cuda.synchronize(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            a = hs.random_action()          # D2H: 4 B/board
+            hs.step(a)                      # H2D: 4 B/board; D2H: obs 81 + reward 4 + flags 1 B/board
+        torch.cuda.synchronize(dev)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e = {"value": world * n * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes + n * 4,
+               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "api": "HostStepper.random_action() + HostStepper.step(actions_host) -> (obs u8, reward, done, won) "
+                      "in pinned host memory, 8 chunks pipelined over CUDA streams"}
+        del hs
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_rate(12.0)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        avg_launch_ms = sum(per_launch) / len(per_launch)
+        achieved = BYTES_PER_STEP * n / (avg_launch_ms * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                         "kernel": "step_kernel<Shape<9,9,3,false>, philox>",
+                         "algorithmic_bytes_per_launch": BYTES_PER_STEP * n, "avg_launch_ms": avg_launch_ms,
+                         "peak_source": peak_src,
+                         "note": "integer-issue bound, not HBM bound (DESIGN.md): the HBM fraction is reported as required"},
+            "cpu_baseline": cpu,
+            "run": {"mean_cascades_per_step": mean_casc, "boards_without_legal_move": stuck, "boards_flagged": bad,
+                    "episode_stats": stats},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,277 @@
+"""BatchedBoards: N match-3 boards resident on one GPU, stepped in lockstep by libecg.so.
+
+This is the batched counterpart of the reference's `BoardV2` (match3tile/boardv2.py:11-226): the same
+vocabulary (`array`, `legal_actions`, `apply_action`, `reward`, `n_actions`, `is_terminal`, `clone`,
+`greedy_action`) with a leading board dimension.  PyTorch tensors are only the device buffers; all
+board logic runs in the CUDA kernels behind the C-ABI (include/ecg.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import secrets
+
+import torch
+
+from . import _native as N
+from .config import BoardConfig
+
+_I32_MAX = 2 ** 31 - 1
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class BatchedBoards:
+    """num_boards boards of one BoardConfig on `device`.
+
+    refill="philox": refill tiles, shuffles and random picks come from Philox4x32-10 keyed by
+        (key, board0 + i, step) -- results do not depend on how the batch is sharded over GPUs.
+    refill="replay": board i replays numpy's legacy MT19937 stream of seeds[i] exactly like the
+        reference (np.random.seed(cfg.seed) at the top of every apply_action, boardv2.py:46), which
+        makes trajectories bit-identical to BoardV2 / samplerTasks.random_task.
+    """
+
+    def __init__(self, cfg: BoardConfig, num_boards: int, n_actions: int = 20, *, device=None, refill="philox",
+                 key=None, seeds=None, board0: int = 0, stream_len: int = 4096, arrays=None,
+                 env_goal: int = _I32_MAX, _empty=False):
+        if not torch.cuda.is_available():
+            raise N.EcgError("BatchedBoards needs a CUDA device (no CPU fallback)")
+        self.L = N.lib()
+        self.cfg = cfg
+        self.nat = cfg.native
+        self.n = int(num_boards)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.env_goal = int(env_goal)
+        self.refill_mode = refill
+        self.board0 = int(board0)
+        self.step_ctr = 0
+        self.key = int(key if key is not None else (cfg.seed if refill == "philox" else 0)) & (2 ** 64 - 1)
+        self.stream = None
+        self.stream_pos = None
+        self.stream_len = 0
+        self.stream_stride = 0
+        dev = self.device
+        nb = self.L.ecg_boards_bytes(C.byref(self.nat), self.n) // 4
+        nm = self.L.ecg_masks_bytes(C.byref(self.nat), self.n) // 4
+        self.boards = torch.zeros(nb, dtype=torch.int32, device=dev)
+        self.mask = torch.zeros(nm, dtype=torch.int32, device=dev)
+        self._mask_valid = False
+        self.moves_left = torch.full((self.n,), int(n_actions), dtype=torch.int32, device=dev)
+        self.score = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.step_reward = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.cascades = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.flags = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+        self.last_actions = torch.full((self.n,), -1, dtype=torch.int32, device=dev)
+        if _empty:
+            return
+        if refill == "replay":
+            if seeds is None:
+                seeds = [cfg.seed] * 1  # one shared stream: every board replays cfg.seed (MCTS leaves do)
+            seeds_t = torch.as_tensor(seeds, dtype=torch.int64).reshape(-1)
+            if seeds_t.numel() not in (1, self.n):
+                raise ValueError("seeds must hold one seed (shared stream) or one per board")
+            self.seeds = seeds_t.clone()
+            sd = seeds_t.to(dev).to(torch.int32)
+            self.stream_len = int(stream_len)
+            self.stream = torch.empty(sd.numel() * self.stream_len, dtype=torch.int32, device=dev)
+            N.check(self.L.ecg_mt19937_stream(_ptr(sd), _ptr(self.stream), self.stream_len, sd.numel(), _stream(dev)),
+                    "ecg_mt19937_stream")
+            self.stream_stride = self.stream_len if sd.numel() == self.n and self.n > 1 else 0
+            self.stream_pos = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        elif refill != "philox":
+            raise ValueError("refill must be 'philox' or 'replay'")
+        if arrays is not None:
+            self.set_arrays(arrays)
+        else:
+            rf = self._refill()
+            N.check(self.L.ecg_init_boards(C.byref(self.nat), C.byref(rf), _ptr(self.boards), _ptr(self.status),
+                                           self.n, _stream(dev)), "ecg_init_boards")
+
+    # ------------------------------------------------------------------ plumbing
+    def _refill(self, step_ctr=None) -> N.Refill:
+        rf = N.Refill()
+        if self.refill_mode == "philox":
+            rf.mode = N.REFILL_PHILOX
+            rf.philox_key = self.key
+            rf.board0 = self.board0
+            rf.step_ctr = (self.step_ctr if step_ctr is None else step_ctr) & 0xFFFFFFFF
+        else:
+            rf.mode = N.REFILL_REPLAY
+            rf.stream = self.stream.data_ptr()
+            rf.stream_len = self.stream_len
+            rf.stream_stride = self.stream_stride
+            rf.stream_pos = self.stream_pos.data_ptr()
+        return rf
+
+    def set_arrays(self, arrays):
+        """Load boards from [N, rows, cols] cell values (BoardV2.array convention)."""
+        a = torch.as_tensor(arrays)
+        if a.dtype not in (torch.int64, torch.uint8):
+            a = a.to(torch.int64)
+        a = a.to(self.device).contiguous()
+        if tuple(a.shape) != (self.n, self.cfg.rows, self.cfg.columns):
+            raise ValueError(f"expected shape {(self.n, self.cfg.rows, self.cfg.columns)}, got {tuple(a.shape)}")
+        N.check(self.L.ecg_pack(C.byref(self.nat), _ptr(a), a.element_size(), _ptr(self.boards), _ptr(self.status),
+                                self.n, _stream(self.device)), "ecg_pack")
+        self._mask_valid = False
+        if bool((self.status & N.ST_BAD_CELL).any()):
+            raise ValueError("cell value outside {0, 1..min(type_mask, 11), h_line, v_line, bomb, mega_token}")
+
+    # ------------------------------------------------------------------ BoardV2 surface
+    @property
+    def array(self) -> torch.Tensor:
+        """int64 [N, rows, cols]: BoardV2.array of every board"""
+        return self.observe(torch.int64)
+
+    def observe(self, dtype=torch.uint8, out=None) -> torch.Tensor:
+        if dtype not in (torch.uint8, torch.int64):
+            raise ValueError("dtype must be torch.uint8 or torch.int64")
+        if out is None:
+            out = torch.empty((self.n, self.cfg.rows, self.cfg.columns), dtype=dtype, device=self.device)
+        N.check(self.L.ecg_unpack(C.byref(self.nat), _ptr(self.boards), _ptr(out), out.element_size(), self.n,
+                                  _stream(self.device)), "ecg_unpack")
+        return out
+
+    def packed_mask(self) -> torch.Tensor:
+        """packed legal mask of the current boards (computed by the step kernel; recomputed only after
+        set_arrays / construction)"""
+        if not self._mask_valid:
+            N.check(self.L.ecg_legal_mask(C.byref(self.nat), _ptr(self.boards), _ptr(self.mask), self.n,
+                                          _stream(self.device)), "ecg_legal_mask")
+            self._mask_valid = True
+        return self.mask
+
+    def legal_mask(self, out=None) -> torch.Tensor:
+        """bool [N, action_space]; row i is the membership vector of BoardV2.legal_actions of board i"""
+        m = self.packed_mask()
+        if out is None:
+            out = torch.empty((self.n, self.cfg.action_space), dtype=torch.bool, device=self.device)
+        N.check(self.L.ecg_unpack_mask(C.byref(self.nat), _ptr(m), _ptr(out), self.n, _stream(self.device)),
+                "ecg_unpack_mask")
+        return out
+
+    @property
+    def legal_actions(self):
+        """list (per board) of ascending action lists, like BoardV2.legal_actions (boardv2.py:31-35)"""
+        m = self.legal_mask().cpu()
+        return [torch.nonzero(row, as_tuple=False).flatten().tolist() for row in m]
+
+    def random_action(self, out=None) -> torch.Tensor:
+        """int32 [N]: a uniformly random legal action per board (README's env.board.random_action(),
+        = np.random.choice(state.legal_actions), samplerTasks.py:13); -1 where no action is legal"""
+        m = self.packed_mask()
+        if out is None:
+            out = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        rf = self._refill()
+        N.check(self.L.ecg_random_action(C.byref(self.nat), C.byref(rf), _ptr(m), _ptr(out), None, self.n,
+                                         _stream(self.device)), "ecg_random_action")
+        return out
+
+    def apply_action(self, actions=None) -> "BatchedBoards":
+        """One lockstep BoardV2.apply_action (boardv2.py:43-207) on every board, IN PLACE.
+        actions: int tensor/array [N]; None = each board plays a uniformly random legal action.
+        Afterwards: step_reward, score (cumulative = BoardV2.reward), cascades, moves_left, flags, status,
+        last_actions and the legal mask describe the new state."""
+        io = N.StepIO()
+        if actions is None:
+            io.mask_in = self.packed_mask().data_ptr()
+            keep = None
+        else:
+            keep = torch.as_tensor(actions).to(device=self.device, dtype=torch.int32).contiguous()
+            if keep.numel() != self.n:
+                raise ValueError("one action per board")
+            io.actions = keep.data_ptr()
+        io.boards_in = io.boards_out = self.boards.data_ptr()
+        io.actions_out = self.last_actions.data_ptr()
+        io.moves_left = self.moves_left.data_ptr()
+        io.reward = self.step_reward.data_ptr()
+        io.score = self.score.data_ptr()
+        io.cascades = self.cascades.data_ptr()
+        io.mask_out = self.mask.data_ptr()
+        io.flags = self.flags.data_ptr()
+        io.status = self.status.data_ptr()
+        io.env_goal = self.env_goal
+        rf = self._refill()
+        N.check(self.L.ecg_step(C.byref(self.nat), C.byref(rf), C.byref(io), self.n, _stream(self.device)), "ecg_step")
+        self._mask_valid = True
+        self.step_ctr += 1
+        return self
+
+    def rollout(self) -> torch.Tensor:
+        """Play uniformly random legal actions until every board is terminal, in ONE kernel
+        (MCTS.rollout, mctslib/standard/mcts.py:14-19; samplerTasks.random_task :9-14).
+        Returns int64 [N] points collected; score / moves_left / boards are updated in place."""
+        total = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        steps = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        rf = self._refill()
+        N.check(self.L.ecg_rollout(C.byref(self.nat), C.byref(rf), _ptr(self.boards), _ptr(self.moves_left),
+                                   _ptr(total), _ptr(steps), _ptr(self.status), self.n, _stream(self.device)),
+                "ecg_rollout")
+        self.step_ctr += int(self.moves_left.max().item()) if self.n else 0
+        self.score += total.to(torch.int32)
+        self.moves_left -= steps
+        self._mask_valid = False
+        self.rollout_steps = steps
+        return total
+
+    @property
+    def reward(self) -> torch.Tensor:
+        """cumulative reward per board (BoardV2.reward, boardv2.py:224-226)"""
+        return self.score.to(torch.int64)
+
+    @property
+    def n_actions(self) -> torch.Tensor:
+        return self.moves_left
+
+    @property
+    def is_terminal(self) -> torch.Tensor:
+        """boardv2.py:220-222"""
+        return self.moves_left < 1
+
+    def clone(self) -> "BatchedBoards":
+        c = BatchedBoards(self.cfg, self.n, device=self.device, refill=self.refill_mode, key=self.key,
+                          board0=self.board0, env_goal=self.env_goal, _empty=True)
+        for name in ("boards", "mask", "moves_left", "score", "step_reward", "cascades", "flags", "status",
+                     "last_actions"):
+            getattr(c, name).copy_(getattr(self, name))
+        c._mask_valid = self._mask_valid
+        c.step_ctr = self.step_ctr
+        c.stream, c.stream_len, c.stream_stride = self.stream, self.stream_len, self.stream_stride  # read-only, shared
+        c.stream_pos = None if self.stream_pos is None else self.stream_pos.clone()
+        return c
+
+    def greedy_action(self) -> torch.Tensor:
+        """argmax over legal actions of the one-step reward, first maximum wins (boardv2.py:209-218).
+        Expands all children: one step kernel per action id over cloned boards."""
+        legal = self.legal_mask()
+        best = torch.full((self.n,), -1, dtype=torch.int32, device=self.device)
+        best_r = torch.full((self.n,), -1, dtype=torch.int64, device=self.device)
+        for a in range(self.cfg.action_space):
+            col = legal[:, a]
+            if not bool(col.any()):
+                continue
+            child = self.clone()
+            child.apply_action(torch.full((self.n,), a, dtype=torch.int32, device=self.device))
+            r = torch.where(col, child.reward, torch.full_like(best_r, -1))
+            better = r > best_r
+            best = torch.where(better, torch.full_like(best, a), best)
+            best_r = torch.where(better, r, best_r)
+        return best
+
+    # ------------------------------------------------------------------ statistics
+    def episode_stats(self) -> torch.Tensor:
+        """int64[6] on device: sum(score), n, min, max, wins, sum(score^2) (main.py:240-267 sample())"""
+        out = torch.tensor([0, 0, 2 ** 63 - 1, -2 ** 63, 0, 0], dtype=torch.int64, device=self.device)
+        N.check(self.L.ecg_episode_stats(_ptr(self.score), _ptr(self.flags), _ptr(out), self.n, _stream(self.device)),
+                "ecg_episode_stats")
+        return out
+
+
+def fresh_key() -> int:
+    return secrets.randbits(63)

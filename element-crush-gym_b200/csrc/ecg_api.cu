@@ -1,0 +1,289 @@
+// ecg_api.cu -- the C-ABI of libecg.so (include/ecg.h): argument checks, dispatch to the per-size
+// kernel objects (ecg_shape_kernels.cu), and the two size-independent kernels.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/ecg.h"
+#include "ecg_core.cuh"
+#include "ecg_ops.h"
+
+using namespace ecg;
+
+static_assert(ECG_ST_TERMINAL == ST_TERMINAL && ECG_ST_STREAM_OVERFLOW == ST_STREAM_OVERFLOW &&
+                  ECG_ST_SHUFFLE_CAP == ST_SHUFFLE_CAP && ECG_ST_BAD_ACTION == ST_BAD_ACTION &&
+                  ECG_ST_NO_LEGAL == ST_NO_LEGAL && ECG_ST_BAD_CELL == ST_BAD_CELL &&
+                  ECG_ST_CASCADE_CAP == ST_CASCADE_CAP,
+              "status bits of include/ecg.h and ecg_core.cuh must agree");
+
+namespace {
+
+thread_local char g_err[256] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return -1;
+}
+int check_launch(const char *what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return -2;
+    }
+    return 0;
+}
+
+inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// numpy legacy MT19937: init_genrand(seed) then genrand_int32; thread-local state
+__global__ void __launch_bounds__(64) mt19937_kernel(const uint32_t *__restrict__ seeds, uint32_t *__restrict__ out,
+                                                     int len, long long n) {
+    const long long i = (long long)blockIdx.x * 64 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t mt[624];
+    mt[0] = seeds[i];
+    for (int k = 1; k < 624; k++) mt[k] = 1812433253u * (mt[k - 1] ^ (mt[k - 1] >> 30)) + (uint32_t)k;
+    int mti = 624;
+    uint32_t *dst = out + i * len;
+    for (int j = 0; j < len; j++) {
+        if (mti >= 624) {
+            for (int k = 0; k < 624; k++) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            mti = 0;
+        }
+        uint32_t y = mt[mti++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        dst[j] = y;
+    }
+}
+
+__global__ void __launch_bounds__(256) stats_kernel(const int32_t *__restrict__ score, const uint8_t *__restrict__ flags,
+                                                    long long *out, long long n) {
+    long long sum = 0, sq = 0, cnt = 0, wins = 0, mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long s = score[i];
+        sum += s;
+        sq += s * s;
+        cnt++;
+        mn = s < mn ? s : mn;
+        mx = s > mx ? s : mx;
+        if (flags && (flags[i] & ECG_FLAG_WON)) wins++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        sq += __shfl_down_sync(0xffffffffu, sq, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        wins += __shfl_down_sync(0xffffffffu, wins, o);
+        const long long a = __shfl_down_sync(0xffffffffu, mn, o), b = __shfl_down_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long *)&out[0], (unsigned long long)sum);
+        atomicAdd((unsigned long long *)&out[1], (unsigned long long)cnt);
+        atomicMin(&out[2], mn);
+        atomicMax(&out[3], mx);
+        atomicAdd((unsigned long long *)&out[4], (unsigned long long)wins);
+        atomicAdd((unsigned long long *)&out[5], (unsigned long long)sq);
+    }
+}
+
+
+RefillDev to_dev(const ecg_refill *rf) {
+    RefillDev d;
+    d.stream = rf->stream;
+    d.stream_stride = rf->stream_stride;
+    d.stream_pos = rf->stream_pos;
+    d.key = rf->philox_key;
+    d.board0 = rf->board0;
+    d.step_ctr = rf->step_ctr;
+    d.stream_len = rf->stream_len;
+    return d;
+}
+
+const ShapeOps *ops_for(int rows) {
+    switch (rows) {
+    case 5: return shape_ops_5();
+    case 6: return shape_ops_6();
+    case 7: return shape_ops_7();
+    case 9: return shape_ops_9();
+    case 12: return shape_ops_12();
+    case 16: return shape_ops_16();
+    default: return nullptr;
+    }
+}
+
+int check_cfg(const ecg_config *cfg) {
+    if (!cfg) return fail("cfg is NULL");
+    ecg_config ref;
+    if (ecg_config_init(&ref, cfg->rows, cfg->cols, cfg->types) != 0) return -1;
+    if (memcmp(&ref, cfg, sizeof(ref)) != 0) return fail("ecg_config was not produced by ecg_config_init");
+    return 0;
+}
+int check_refill(const ecg_refill *rf) {
+    if (!rf) return fail("refill is NULL");
+    if (rf->mode == ECG_REFILL_PHILOX) return 0;
+    if (rf->mode == ECG_REFILL_REPLAY) {
+        if (!rf->stream || rf->stream_len <= 0 || rf->stream_stride < 0)
+            return fail("replay refill needs stream, stream_len > 0, stream_stride >= 0");
+        return 0;
+    }
+    return fail("refill mode must be ECG_REFILL_REPLAY or ECG_REFILL_PHILOX");
+}
+
+} // namespace
+
+extern "C" {
+
+int ecg_version(void) { return ECG_VERSION; }
+const char *ecg_last_error(void) { return g_err; }
+int64_t ecg_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+int ecg_config_init(ecg_config *cfg, int rows, int cols, int types) {
+    if (!cfg) return fail("cfg is NULL");
+    if (rows != cols)
+        return fail("only square boards: the reference's action space rows*(cols-1)*2 (boardConfig.py:27) is wrong otherwise");
+    if (!ops_for(rows)) return fail("board size must be one of 5, 6, 7, 9, 12, 16");
+    if (types < 1 || types > 11) return fail("types must be in 1..11 (4-bit cell codes)");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->rows = rows;
+    cfg->cols = cols;
+    cfg->types = types;
+    int bits = 0;
+    while ((1 << bits) < types + 1) bits++;
+    cfg->bits = bits;
+    cfg->type_mask = (1 << bits) - 1;
+    cfg->special_type_mask = (1 << (bits + 1)) + 1 + cfg->type_mask;
+    cfg->h_line = cfg->type_mask + 1;
+    cfg->v_line = 2 * cfg->h_line;
+    cfg->bomb = cfg->special_type_mask;
+    cfg->mega_token = cfg->type_mask + cfg->special_type_mask + 1;
+    cfg->action_space = rows * (cols - 1) * 2;
+    cfg->board_words = 4 * ((rows * (cols + 1) + 31) / 32);
+    cfg->mask_words = (cfg->action_space + 31) / 32;
+    return 0;
+}
+
+int64_t ecg_boards_bytes(const ecg_config *cfg, int64_t n) {
+    return ((n + ECG_TILE - 1) / ECG_TILE) * ECG_TILE * (int64_t)cfg->board_words * 4;
+}
+int64_t ecg_masks_bytes(const ecg_config *cfg, int64_t n) {
+    return ((n + ECG_TILE - 1) / ECG_TILE) * ECG_TILE * (int64_t)cfg->mask_words * 4;
+}
+
+int ecg_pack(const ecg_config *cfg, const void *cells, int elem_bytes, void *boards, uint8_t *status, int64_t n,
+             void *stream) {
+    if (check_cfg(cfg)) return -1;
+    if (!cells || !boards) return fail("ecg_pack: NULL buffer");
+    if (elem_bytes != 8 && elem_bytes != 1) return fail("ecg_pack: elem_bytes must be 8 (int64) or 1 (uint8)");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->pack(cfg->types >= 8, cells, elem_bytes, boards, status, cfg->types, n, (cudaStream_t)stream);
+    return check_launch("ecg_pack");
+}
+
+int ecg_unpack(const ecg_config *cfg, const void *boards, void *cells, int elem_bytes, int64_t n, void *stream) {
+    if (check_cfg(cfg)) return -1;
+    if (!cells || !boards) return fail("ecg_unpack: NULL buffer");
+    if (elem_bytes != 8 && elem_bytes != 1) return fail("ecg_unpack: elem_bytes must be 8 (int64) or 1 (uint8)");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->unpack(cfg->types >= 8, boards, cells, elem_bytes, cfg->types, n, (cudaStream_t)stream);
+    return check_launch("ecg_unpack");
+}
+
+int ecg_unpack_mask(const ecg_config *cfg, const uint32_t *mask, uint8_t *out, int64_t n, void *stream) {
+    if (check_cfg(cfg)) return -1;
+    if (!mask || !out) return fail("ecg_unpack_mask: NULL buffer");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->unpack_mask(mask, out, n, (cudaStream_t)stream);
+    return check_launch("ecg_unpack_mask");
+}
+
+int ecg_mt19937_stream(const uint32_t *seeds, uint32_t *out, int32_t len, int64_t n, void *stream) {
+    if (!seeds || !out || len <= 0) return fail("ecg_mt19937_stream: bad argument");
+    if (n <= 0) return 0;
+    mt19937_kernel<<<grid_for(n, 64), 64, 0, (cudaStream_t)stream>>>(seeds, out, len, n);
+    return check_launch("ecg_mt19937_stream");
+}
+
+int ecg_init_boards(const ecg_config *cfg, const ecg_refill *rf, void *boards, uint8_t *status, int64_t n,
+                    void *stream) {
+    if (check_cfg(cfg) || check_refill(rf)) return -1;
+    if (!boards) return fail("ecg_init_boards: NULL buffer");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->init(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), boards, status, cfg->types, n,
+                             (cudaStream_t)stream);
+    return check_launch("ecg_init_boards");
+}
+
+int ecg_legal_mask(const ecg_config *cfg, const void *boards, uint32_t *mask, int64_t n, void *stream) {
+    if (check_cfg(cfg)) return -1;
+    if (!boards || !mask) return fail("ecg_legal_mask: NULL buffer");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->legal(cfg->types >= 8, boards, mask, n, (cudaStream_t)stream);
+    return check_launch("ecg_legal_mask");
+}
+
+int ecg_random_action(const ecg_config *cfg, const ecg_refill *rf, const uint32_t *mask, int32_t *actions,
+                      uint8_t *status, int64_t n, void *stream) {
+    if (check_cfg(cfg) || check_refill(rf)) return -1;
+    if (!mask || !actions) return fail("ecg_random_action: NULL buffer");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->random_action(rf->mode == ECG_REFILL_PHILOX, to_dev(rf), mask, actions, status, n,
+                                      (cudaStream_t)stream);
+    return check_launch("ecg_random_action");
+}
+
+int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io, int64_t n, void *stream) {
+    if (check_cfg(cfg) || check_refill(rf)) return -1;
+    if (!io || !io->boards_in || !io->boards_out) return fail("ecg_step: boards_in/boards_out are required");
+    if (!io->actions && !io->mask_in) return fail("ecg_step: actions == NULL needs mask_in (random legal action)");
+    if (io->flags && !(io->score && io->moves_left)) return fail("ecg_step: flags need score and moves_left");
+    if (n <= 0) return 0;
+    StepDev sd;
+    sd.boards_in = io->boards_in;
+    sd.boards_out = io->boards_out;
+    sd.actions = io->actions;
+    sd.mask_in = io->mask_in;
+    sd.actions_out = io->actions_out;
+    sd.moves_left = io->moves_left;
+    sd.reward = io->reward;
+    sd.score = io->score;
+    sd.cascades = io->cascades;
+    sd.mask_out = io->mask_out;
+    sd.flags = io->flags;
+    sd.status = io->status;
+    sd.env_goal = io->env_goal;
+    sd.types = cfg->types;
+    ops_for(cfg->rows)->step(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), sd, n, (cudaStream_t)stream);
+    return check_launch("ecg_step");
+}
+
+int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
+                int64_t *total_reward, int32_t *steps_done, uint8_t *status, int64_t n, void *stream) {
+    if (check_cfg(cfg) || check_refill(rf)) return -1;
+    if (!boards || !moves_left || !total_reward) return fail("ecg_rollout: boards, moves_left and total_reward are required");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->rollout(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), boards, moves_left,
+                                (long long *)total_reward, steps_done, status, cfg->types, n, (cudaStream_t)stream);
+    return check_launch("ecg_rollout");
+}
+
+int ecg_episode_stats(const int32_t *score, const uint8_t *flags, int64_t *out, int64_t n, void *stream) {
+    if (!score || !out) return fail("ecg_episode_stats: NULL buffer");
+    if (n <= 0) return 0;
+    unsigned g = grid_for(n, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    stats_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(score, flags, (long long *)out, n);
+    return check_launch("ecg_episode_stats");
+}
+}

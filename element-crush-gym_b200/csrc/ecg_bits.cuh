@@ -15,7 +15,9 @@
 #if defined(__CUDACC__)
 #define ECG_HD __host__ __device__ __forceinline__
 #define ECG_HD_NOINLINE __host__ __device__ __noinline__
+#define ECG_HD_CONSTEXPR __host__ __device__ constexpr
 #else
+#define ECG_HD_CONSTEXPR constexpr
 #define ECG_HD inline __attribute__((always_inline))
 #define ECG_HD_NOINLINE __attribute__((noinline))
 #endif
@@ -238,7 +240,7 @@ struct Geo {
     static_assert(C_ >= 4 && C_ <= 16, "boardConfig.decode (:50) needs columns >= 4; 16 is the engine's limit");
 
     // word i of the set { bit r*S + c : r0 <= r < r1, c0 <= c < c1 }
-    static constexpr uint32_t rect_word(int i, int r0, int r1, int c0, int c1) {
+    static ECG_HD_CONSTEXPR uint32_t rect_word(int i, int r0, int r1, int c0, int c1) {
         uint32_t m = 0;
         for (int r = r0; r < r1; r++)
             for (int c = c0; c < c1; c++) {

@@ -1,0 +1,53 @@
+// ecg_ops.h -- internal seam between the per-size kernel objects (ecg_shape_kernels.cu, one
+// object per -DECG_SIZE) and the C-ABI (ecg_api.cu).  Not installed; not part of include/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ecg {
+
+struct RefillDev {
+    const uint32_t *stream;
+    long long stream_stride;
+    uint32_t *stream_pos;
+    unsigned long long key, board0;
+    uint32_t step_ctr;
+    int stream_len;
+};
+
+struct StepDev {
+    const void *boards_in;
+    void *boards_out;
+    const int32_t *actions;
+    const uint32_t *mask_in;
+    int32_t *actions_out, *moves_left, *reward, *score, *cascades;
+    uint32_t *mask_out;
+    uint8_t *flags, *status;
+    int env_goal, types;
+};
+
+// `wide` selects the types >= 8 instantiation (4 token planes + np.clip(.., 0, 32) quirk)
+struct ShapeOps {
+    void (*pack)(bool wide, const void *cells, int elem_bytes, void *boards, uint8_t *status, int types, long long n,
+                 cudaStream_t s);
+    void (*unpack)(bool wide, const void *boards, void *cells, int elem_bytes, int types, long long n, cudaStream_t s);
+    void (*unpack_mask)(const uint32_t *mask, uint8_t *out, long long n, cudaStream_t s);
+    void (*init)(bool wide, bool philox, RefillDev rf, void *boards, uint8_t *status, int types, long long n,
+                 cudaStream_t s);
+    void (*legal)(bool wide, const void *boards, uint32_t *mask, long long n, cudaStream_t s);
+    void (*random_action)(bool philox, RefillDev rf, const uint32_t *mask, int32_t *actions, uint8_t *status,
+                          long long n, cudaStream_t s);
+    void (*step)(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s);
+    void (*rollout)(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left,
+                    long long *total_reward, int32_t *steps_done, uint8_t *status, int types, long long n,
+                    cudaStream_t s);
+};
+
+const ShapeOps *shape_ops_5();
+const ShapeOps *shape_ops_6();
+const ShapeOps *shape_ops_7();
+const ShapeOps *shape_ops_9();
+const ShapeOps *shape_ops_12();
+const ShapeOps *shape_ops_16();
+
+} // namespace ecg

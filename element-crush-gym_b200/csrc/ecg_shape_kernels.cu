@@ -1,0 +1,411 @@
+// ecg_shape_kernels.cu -- sm_100a kernels of libecg.so for ONE board size (compiled once per
+// -DECG_SIZE=N so the sizes build in parallel); ecg_api.cu holds the C-ABI (include/ecg.h).
+//
+// One thread owns one board for the whole step: the board is 4 bit-planes x W words
+// (12 registers for 9x9), every operation is a 32-bit integer op on those registers
+// (LOP3 / SHF / IADD3 / POPC), no shared memory, no shuffles, no tensor cores.
+//
+// HBM layout ("tile-interleaved"): boards are grouped in tiles of 32; inside a tile the
+// 16-byte chunk k of board `lane` sits at uint4 index (tile*CH + k)*32 + lane, so one warp
+// moves a whole tile with CH fully coalesced 512-byte LDG.128/STG.128 transactions.
+// Legal masks use the same tiling with 4-byte words: u32 index (tile*MW + w)*32 + lane.
+#include <cuda_runtime.h>
+
+#include "../../include/ecg.h"
+#include "ecg_core.cuh"
+#include "ecg_ops.h"
+
+#ifndef ECG_SIZE
+#error "compile with -DECG_SIZE=<board size>"
+#endif
+
+using namespace ecg;
+
+static_assert(ECG_ST_TERMINAL == ST_TERMINAL && ECG_ST_STREAM_OVERFLOW == ST_STREAM_OVERFLOW &&
+                  ECG_ST_SHUFFLE_CAP == ST_SHUFFLE_CAP && ECG_ST_BAD_ACTION == ST_BAD_ACTION &&
+                  ECG_ST_NO_LEGAL == ST_NO_LEGAL && ECG_ST_BAD_CELL == ST_BAD_CELL &&
+                  ECG_ST_CASCADE_CAP == ST_CASCADE_CAP,
+              "status bits of include/ecg.h and ecg_core.cuh must agree");
+
+namespace {
+
+constexpr int BLOCK = 128;
+
+
+// ------------------------------------------------------------------ packed I/O
+
+template <class G>
+__device__ __forceinline__ void load_board(const void *boards, long long i, Board<G> &b) {
+    constexpr int BW = 4 * G::W, CH = BW / 4;
+    const uint4 *base = reinterpret_cast<const uint4 *>(boards) + (i >> 5) * (CH * 32) + (i & 31);
+    uint32_t w[BW];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        const uint4 v = __ldcs(base + k * 32);
+        w[4 * k] = v.x;
+        w[4 * k + 1] = v.y;
+        w[4 * k + 2] = v.z;
+        w[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int j = 0; j < G::W; j++) b.p[p].w[j] = w[p * G::W + j];
+}
+
+template <class G>
+__device__ __forceinline__ void store_board(void *boards, long long i, const Board<G> &b) {
+    constexpr int BW = 4 * G::W, CH = BW / 4;
+    uint4 *base = reinterpret_cast<uint4 *>(boards) + (i >> 5) * (CH * 32) + (i & 31);
+    uint32_t w[BW];
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int j = 0; j < G::W; j++) w[p * G::W + j] = b.p[p].w[j];
+#pragma unroll
+    for (int k = 0; k < CH; k++) __stcs(base + k * 32, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
+}
+
+template <class G>
+__device__ __forceinline__ void load_mask(const uint32_t *mask, long long i, uint32_t m[G::AW]) {
+    const uint32_t *base = mask + (i >> 5) * (G::AW * 32) + (i & 31);
+#pragma unroll
+    for (int k = 0; k < G::AW; k++) m[k] = __ldcs(base + k * 32);
+}
+template <class G>
+__device__ __forceinline__ void store_mask(uint32_t *mask, long long i, const uint32_t m[G::AW]) {
+    uint32_t *base = mask + (i >> 5) * (G::AW * 32) + (i & 31);
+#pragma unroll
+    for (int k = 0; k < G::AW; k++) __stcs(base + k * 32, m[k]);
+}
+
+template <class SH>
+__device__ __forceinline__ void legal_of(const Board<typename SH::G> &b, BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    using G = typename SH::G;
+    const Derived<G> d = derive<SH>(b);
+    legal_swaps<SH>(d, eq_at<SH, 1>(d), eq_at<SH, G::S>(d), HL, VL);
+}
+
+// ------------------------------------------------------------------ kernels
+
+template <class SH, typename T>
+__global__ void __launch_bounds__(BLOCK) pack_kernel(const T *__restrict__ cells, void *boards, uint8_t *status,
+                                                     int types, long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const CellCodec cc = make_codec(types);
+    const T *src = cells + i * (G::R * G::C);
+    Board<G> b;
+#pragma unroll
+    for (int k = 0; k < 4; k++) b.p[k] = bb_zero<G::W>();
+    uint32_t st = 0;
+    for (int r = 0; r < G::R; r++)
+        for (int c = 0; c < G::C; c++) {
+            int code = encode_cell(cc, (long long)src[r * G::C + c]);
+            if (code < 0) {
+                st = ST_BAD_CELL;
+                code = 0;
+            }
+            set_code(b, r * G::S + c, code);
+        }
+    store_board<G>(boards, i, b);
+    if (status) status[i] = (uint8_t)st;
+}
+
+template <class SH, typename T>
+__global__ void __launch_bounds__(BLOCK) unpack_kernel(const void *boards, T *__restrict__ cells, int types,
+                                                       long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const CellCodec cc = make_codec(types);
+    Board<G> b;
+    load_board<G>(boards, i, b);
+    T *dst = cells + i * (G::R * G::C);
+    for (int r = 0; r < G::R; r++)
+        for (int c = 0; c < G::C; c++) dst[r * G::C + c] = (T)decode_cell(cc, cell_code<G>(b, r * G::S + c));
+}
+
+template <class SH>
+__global__ void __launch_bounds__(BLOCK) unpack_mask_kernel(const uint32_t *mask, uint8_t *__restrict__ out,
+                                                            long long n) {
+    using G = typename SH::G;
+    // one thread per (board, action): coalesced byte stores
+    const long long t = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (t >= n * G::A) return;
+    const long long i = t / G::A;
+    const int a = (int)(t - i * G::A);
+    const uint32_t w = mask[(i >> 5) * (G::AW * 32) + (a >> 5) * 32 + (i & 31)];
+    out[t] = (w >> (a & 31)) & 1u;
+}
+
+template <class SH>
+__global__ void __launch_bounds__(BLOCK) legal_kernel(const void *boards, uint32_t *mask, long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    Board<G> b;
+    load_board<G>(boards, i, b);
+    BB<G::W> HL, VL;
+    legal_of<SH>(b, HL, VL);
+    uint32_t m[G::AW];
+    swaps_to_actions<G>(HL, VL, m);
+    store_mask<G>(mask, i, m);
+}
+
+
+template <bool PHILOX>
+struct RngOf;
+template <>
+struct RngOf<true> {
+    using type = PhiloxRng;
+};
+template <>
+struct RngOf<false> {
+    using type = ReplayRng;
+};
+
+template <class SH, bool PHILOX>
+__global__ void __launch_bounds__(BLOCK) random_action_kernel(RefillDev rf, const uint32_t *mask, int32_t *actions,
+                                                              uint8_t *status, long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    uint32_t m[G::AW];
+    load_mask<G>(mask, i, m);
+    const int cnt = mask_count<G>(m);
+    int a = -1;
+    uint32_t st = 0;
+    if (cnt == 0) {
+        st = ST_NO_LEGAL;
+    } else if (PHILOX) {
+        a = mask_select<G>(m, (int)philox_pick(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr, (uint32_t)cnt));
+    } else {
+        ReplayRng rng;
+        rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
+        a = mask_select<G>(m, (int)rng.below((uint32_t)cnt));
+        if (rf.stream_pos) rf.stream_pos[i] = rng.pos;
+        if (rng.overflow) st = ST_STREAM_OVERFLOW;
+    }
+    actions[i] = a;
+    if (status) status[i] = (uint8_t)st;
+}
+
+template <class SH, bool PHILOX>
+__global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards, uint8_t *status, int types,
+                                                     long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    Board<G> b;
+    typename RngOf<PHILOX>::type rng;
+    if constexpr (PHILOX) rng.init(rf.key, rf.board0 + (unsigned long long)i, 0xFFFFFFFFu);
+    else rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, 0u);
+    init_board<SH>(b, (uint32_t)types, rng);
+    store_board<G>(boards, i, b);
+    if (status) status[i] = rng.overflow ? (uint8_t)ST_STREAM_OVERFLOW : (uint8_t)0;
+}
+
+
+template <class SH, bool PHILOX>
+__global__ void __launch_bounds__(BLOCK) step_kernel(RefillDev rf, StepDev io, long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    Board<G> b;
+    load_board<G>(io.boards_in, i, b);
+    int moves = io.moves_left ? io.moves_left[i] : 1;
+    typename RngOf<PHILOX>::type rng;
+    if constexpr (PHILOX) rng.init(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr);
+    else rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
+
+    StepOut so = {0, 0, 0};
+    int action = -1;
+    if (moves < 1) { // boardv2.py:44
+        so.status = ST_TERMINAL;
+    } else if (io.actions) {
+        action = io.actions[i];
+        if (action < 0 || action >= G::A) {
+            so.status = ST_BAD_ACTION;
+            action = -1;
+        }
+    } else { // board.random_action(): uniform over the legal set of the current board
+        uint32_t m[G::AW];
+        load_mask<G>(io.mask_in, i, m);
+        const int cnt = mask_count<G>(m);
+        if (cnt == 0) {
+            so.status = ST_NO_LEGAL;
+        } else {
+            uint32_t idx;
+            if constexpr (PHILOX) idx = philox_pick(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr, (uint32_t)cnt);
+            else idx = rng.below((uint32_t)cnt);
+            action = mask_select<G>(m, (int)idx);
+        }
+    }
+    BB<G::W> HL, VL;
+    if (action >= 0) {
+        step_board<SH>(b, action, (uint32_t)io.types, rng, so, HL, VL);
+        moves -= 1;
+    } else if (io.mask_out) {
+        legal_of<SH>(b, HL, VL);
+    }
+    if (action >= 0 || io.boards_out != io.boards_in) store_board<G>(io.boards_out, i, b);
+    if (io.mask_out) {
+        uint32_t m[G::AW];
+        swaps_to_actions<G>(HL, VL, m);
+        store_mask<G>(io.mask_out, i, m);
+    }
+    if (io.actions_out) io.actions_out[i] = action;
+    if (io.moves_left) io.moves_left[i] = moves;
+    if (io.reward) io.reward[i] = so.reward;
+    int score = so.reward;
+    if (io.score) {
+        score += io.score[i];
+        io.score[i] = score;
+    }
+    if (io.cascades) io.cascades[i] = so.cascades;
+    if (io.flags) { // env.py:54-55
+        const bool won = score >= io.env_goal;
+        io.flags[i] = (uint8_t)((won || moves == 0 ? ECG_FLAG_DONE : 0) | (won ? ECG_FLAG_WON : 0));
+    }
+    if (io.status) io.status[i] = (uint8_t)so.status;
+    if constexpr (!PHILOX)
+        if (rf.stream_pos) rf.stream_pos[i] = rng.pos;
+}
+
+template <class SH, bool PHILOX>
+__global__ void __launch_bounds__(BLOCK) rollout_kernel(RefillDev rf, void *boards, const int32_t *moves_left,
+                                                        long long *total_reward, int32_t *steps_done, uint8_t *status,
+                                                        int types, long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    Board<G> b;
+    load_board<G>(boards, i, b);
+    int moves = moves_left[i];
+    typename RngOf<PHILOX>::type rng;
+    const unsigned long long board = rf.board0 + (unsigned long long)i;
+    if constexpr (!PHILOX) rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
+    BB<G::W> HL, VL;
+    legal_of<SH>(b, HL, VL);
+    long long total = 0;
+    uint32_t st = 0, step = rf.step_ctr;
+    int done = 0;
+    while (moves >= 1) {
+        uint32_t m[G::AW];
+        swaps_to_actions<G>(HL, VL, m);
+        const int cnt = mask_count<G>(m);
+        if (cnt == 0) {
+            st |= ST_NO_LEGAL;
+            break;
+        }
+        uint32_t idx;
+        if constexpr (PHILOX) {
+            idx = philox_pick(rf.key, board, step, (uint32_t)cnt);
+            rng.init(rf.key, board, step);
+        } else {
+            idx = rng.below((uint32_t)cnt);
+        }
+        const int action = mask_select<G>(m, (int)idx);
+        StepOut so;
+        step_board<SH>(b, action, (uint32_t)types, rng, so, HL, VL);
+        total += so.reward;
+        st |= so.status;
+        moves--;
+        step++;
+        done++;
+        if (st & ST_STREAM_OVERFLOW) break;
+    }
+    store_board<G>(boards, i, b);
+    total_reward[i] = total;
+    if (steps_done) steps_done[i] = done;
+    if (status) status[i] = (uint8_t)st;
+    if constexpr (!PHILOX)
+        if (rf.stream_pos) rf.stream_pos[i] = rng.pos;
+}
+
+// ------------------------------------------------------------------ launchers
+
+inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+using SHN = Shape<ECG_SIZE, ECG_SIZE, 3, false>; // types <= 7
+using SHW = Shape<ECG_SIZE, ECG_SIZE, 4, true>;  // types 8..11
+
+void op_pack(bool wide, const void *cells, int eb, void *boards, uint8_t *status, int types, long long n,
+             cudaStream_t s) {
+    const unsigned g = grid_for(n, BLOCK);
+    if (eb == 8) {
+        if (wide) pack_kernel<SHW, long long><<<g, BLOCK, 0, s>>>((const long long *)cells, boards, status, types, n);
+        else pack_kernel<SHN, long long><<<g, BLOCK, 0, s>>>((const long long *)cells, boards, status, types, n);
+    } else {
+        if (wide) pack_kernel<SHW, uint8_t><<<g, BLOCK, 0, s>>>((const uint8_t *)cells, boards, status, types, n);
+        else pack_kernel<SHN, uint8_t><<<g, BLOCK, 0, s>>>((const uint8_t *)cells, boards, status, types, n);
+    }
+}
+void op_unpack(bool wide, const void *boards, void *cells, int eb, int types, long long n, cudaStream_t s) {
+    const unsigned g = grid_for(n, BLOCK);
+    if (eb == 8) {
+        if (wide) unpack_kernel<SHW, long long><<<g, BLOCK, 0, s>>>(boards, (long long *)cells, types, n);
+        else unpack_kernel<SHN, long long><<<g, BLOCK, 0, s>>>(boards, (long long *)cells, types, n);
+    } else {
+        if (wide) unpack_kernel<SHW, uint8_t><<<g, BLOCK, 0, s>>>(boards, (uint8_t *)cells, types, n);
+        else unpack_kernel<SHN, uint8_t><<<g, BLOCK, 0, s>>>(boards, (uint8_t *)cells, types, n);
+    }
+}
+void op_unpack_mask(const uint32_t *mask, uint8_t *out, long long n, cudaStream_t s) {
+    unpack_mask_kernel<SHN><<<grid_for(n * SHN::G::A, BLOCK), BLOCK, 0, s>>>(mask, out, n);
+}
+void op_init(bool wide, bool philox, RefillDev rf, void *boards, uint8_t *status, int types, long long n,
+             cudaStream_t s) {
+    const unsigned g = grid_for(n, BLOCK);
+    if (wide) {
+        if (philox) init_kernel<SHW, true><<<g, BLOCK, 0, s>>>(rf, boards, status, types, n);
+        else init_kernel<SHW, false><<<g, BLOCK, 0, s>>>(rf, boards, status, types, n);
+    } else {
+        if (philox) init_kernel<SHN, true><<<g, BLOCK, 0, s>>>(rf, boards, status, types, n);
+        else init_kernel<SHN, false><<<g, BLOCK, 0, s>>>(rf, boards, status, types, n);
+    }
+}
+void op_legal(bool wide, const void *boards, uint32_t *mask, long long n, cudaStream_t s) {
+    const unsigned g = grid_for(n, BLOCK);
+    if (wide) legal_kernel<SHW><<<g, BLOCK, 0, s>>>(boards, mask, n);
+    else legal_kernel<SHN><<<g, BLOCK, 0, s>>>(boards, mask, n);
+}
+void op_random_action(bool philox, RefillDev rf, const uint32_t *mask, int32_t *actions, uint8_t *status, long long n,
+                      cudaStream_t s) {
+    const unsigned g = grid_for(n, BLOCK);
+    if (philox) random_action_kernel<SHN, true><<<g, BLOCK, 0, s>>>(rf, mask, actions, status, n);
+    else random_action_kernel<SHN, false><<<g, BLOCK, 0, s>>>(rf, mask, actions, status, n);
+}
+void op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
+    const unsigned g = grid_for(n, BLOCK);
+    if (wide) {
+        if (philox) step_kernel<SHW, true><<<g, BLOCK, 0, s>>>(rf, io, n);
+        else step_kernel<SHW, false><<<g, BLOCK, 0, s>>>(rf, io, n);
+    } else {
+        if (philox) step_kernel<SHN, true><<<g, BLOCK, 0, s>>>(rf, io, n);
+        else step_kernel<SHN, false><<<g, BLOCK, 0, s>>>(rf, io, n);
+    }
+}
+void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left, long long *total_reward,
+                int32_t *steps_done, uint8_t *status, int types, long long n, cudaStream_t s) {
+    const unsigned g = grid_for(n, BLOCK);
+    if (wide) {
+        if (philox) rollout_kernel<SHW, true><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
+        else rollout_kernel<SHW, false><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
+    } else {
+        if (philox) rollout_kernel<SHN, true><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
+        else rollout_kernel<SHN, false><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
+    }
+}
+
+const ShapeOps k_ops = {op_pack, op_unpack, op_unpack_mask, op_init, op_legal, op_random_action, op_step, op_rollout};
+
+} // namespace
+
+#define ECG_CAT2(a, b) a##b
+#define ECG_CAT(a, b) ECG_CAT2(a, b)
+namespace ecg {
+const ShapeOps *ECG_CAT(shape_ops_, ECG_SIZE)() { return &k_ops; }
+} // namespace ecg

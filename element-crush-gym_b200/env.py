@@ -1,0 +1,240 @@
+"""Match3Env contract (match3tile/env.py:8-66) over the batched engine.
+
+The reference's Match3Env is stale (it calls BoardV2 with a `seed=` keyword that no longer exists and
+unpacks apply_action's result), so the *contract* is taken from env.py's text and
+the *semantics* from BoardV2:
+    step(action)  -> (obs, move_score, done, won, {})        env.py:48-56
+    reset(seed)   -> (obs, {})                               env.py:58-65
+    score += move_score; moves_taken += 1; won = score >= env_goal; done = won or moves_taken == num_moves
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .boards import BatchedBoards
+from .config import BoardConfig
+
+
+class BatchedMatch3Env:
+    """num_envs independent Match3Env instances stepped in lockstep on one GPU.
+
+    Same keyword arguments as the reference constructor (env.py:11-20) plus num_envs / device / refill.
+    refill="philox" (default): env i uses Philox substreams (seed, board0 + i).
+    refill="replay": env i is the reference env with seed `seed + i` (numpy MT19937 replay, bit-exact).
+    """
+    metadata = {"render_modes": ["human"], "render_fps": 60, "animation_speed": 1}
+
+    def __init__(self, num_envs: int, width: int = 9, height: int = 9, num_types: int = 6, num_moves: int = 20,
+                 env_goal: int = 500, seed: int = None, render_mode: str = None, *, device=None, refill="philox",
+                 board0: int = 0, stream_len: int = 4096, obs_dtype=torch.uint8):
+        assert width >= 3 and height >= 3, "Board size too small: min size: 3x3"  # env.py:27
+        assert render_mode is None, "rendering (pygame) is outside the engine's scope"
+        self.num_envs = int(num_envs)
+        self.seed = seed if seed is not None else random.randint(1, 2 ** 31 - 1)
+        self.width, self.height, self.num_types = width, height, num_types
+        self.env_goal, self.num_moves = env_goal, num_moves
+        self.action_space = height * (width - 1) + width * (height - 1)  # env.py:36
+        self.render_mode = None
+        self.device, self.refill, self.board0, self.stream_len = device, refill, board0, stream_len
+        self.obs_dtype = obs_dtype
+        self.cfg = BoardConfig(seed=self.seed, rows=height, columns=width, types=num_types)
+        self.board: BatchedBoards = None
+        self._make_board()
+
+    def _make_board(self):
+        kw = dict(device=self.device, refill=self.refill, board0=self.board0, env_goal=self.env_goal)
+        if self.refill == "replay":
+            kw.update(seeds=[(self.seed + i) & 0xFFFFFFFF for i in range(self.num_envs)], stream_len=self.stream_len)
+        else:
+            kw.update(key=self.seed)
+        self.board = BatchedBoards(self.cfg, self.num_envs, self.num_moves, **kw)
+
+    # -- bookkeeping views (env.py:34)
+    @property
+    def score(self):
+        return self.board.score
+
+    @property
+    def moves_taken(self):
+        return self.num_moves - self.board.moves_left
+
+    def init(self):
+        return self.board.observe(self.obs_dtype)
+
+    def reset(self, seed=None):
+        """env.py:58-65.  `(1 + self.seed) % 2**32 - 1` parses as ((1 + seed) % 2**32) - 1 == seed, i.e. a
+        reset without an explicit seed replays the same boards; kept."""
+        if seed is not None:
+            self.seed = seed
+            self.cfg = BoardConfig(seed=self.seed, rows=self.height, columns=self.width, types=self.num_types)
+        self._make_board()
+        return self.board.observe(self.obs_dtype), {}
+
+    def step(self, actions=None):
+        """actions: [num_envs] ints (tensor / ndarray / list) or None for board.random_action().
+        Returns device tensors (obs [N,H,W], reward int32 [N], done bool [N], won bool [N], info)."""
+        b = self.board
+        b.apply_action(actions)
+        obs = b.observe(self.obs_dtype)
+        done = (b.flags & N.FLAG_DONE) != 0
+        won = (b.flags & N.FLAG_WON) != 0
+        return obs, b.step_reward, done, won, {}
+
+    def render(self):
+        return None
+
+
+class HostStepper:
+    """The public call with HOST buffers: actions come from pinned host memory, observation, reward, done
+    and won go back to pinned host memory every step.  The batch is cut into chunks whose H2D copy, step
+    kernel and D2H copies run on separate CUDA streams so PCIe transfers overlap the kernels.
+    bench.py's e2e number is measured through this class."""
+
+    def __init__(self, env: BatchedMatch3Env, chunks: int = 8):
+        self.env = env
+        n = env.num_envs
+        self.n = n
+        dev = env.board.device
+        self.dev = dev
+        chunks = max(1, min(chunks, n // N.TILE or 1))
+        per = -(-n // chunks)
+        per = -(-per // N.TILE) * N.TILE  # whole tiles, so chunk views of the packed buffers stay aligned
+        self.bounds = [(lo, min(lo + per, n)) for lo in range(0, n, per)]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.bounds]
+        R, Cc = env.height, env.width
+        pin = dict(pin_memory=True)
+        self.h_actions = torch.zeros(n, dtype=torch.int32, **pin)
+        self.h_obs = torch.zeros((n, R, Cc), dtype=torch.uint8, **pin)
+        self.h_reward = torch.zeros(n, dtype=torch.int32, **pin)
+        self.h_flags = torch.zeros(n, dtype=torch.uint8, **pin)
+        self.d_actions = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.d_obs = torch.zeros((n, R, Cc), dtype=torch.uint8, device=dev)
+        self.h2d_bytes = n * 4
+        self.d2h_bytes = n * (R * Cc + 4 + 1)
+
+    def _chunk_call(self, lo, hi, fn_step):
+        import ctypes as C
+        b = self.env.board
+        nat = b.nat
+        bw, mw = nat.board_words, nat.mask_words
+        io = N.StepIO()
+        boards = b.boards[lo * bw:]
+        mask = b.mask[lo * mw:]
+        io.boards_in = io.boards_out = boards.data_ptr()
+        io.actions = self.d_actions[lo:].data_ptr()
+        io.actions_out = b.last_actions[lo:].data_ptr()
+        io.moves_left = b.moves_left[lo:].data_ptr()
+        io.reward = b.step_reward[lo:].data_ptr()
+        io.score = b.score[lo:].data_ptr()
+        io.cascades = b.cascades[lo:].data_ptr()
+        io.mask_out = mask.data_ptr()
+        io.flags = b.flags[lo:].data_ptr()
+        io.status = b.status[lo:].data_ptr()
+        io.env_goal = b.env_goal
+        rf = b._refill()
+        rf.board0 = b.board0 + lo
+        if b.refill_mode == "replay":
+            rf.stream = b.stream.data_ptr() + 4 * lo * b.stream_stride
+            rf.stream_pos = b.stream_pos[lo:].data_ptr()
+        return io, rf
+
+    def step(self, actions_host: torch.Tensor = None):
+        """actions_host: pinned int32 [N] (defaults to self.h_actions).  Returns the pinned host tensors
+        (obs uint8 [N,H,W], reward int32 [N], done bool [N], won bool [N], {}) after a full sync."""
+        import ctypes as C
+        env, b = self.env, self.env.board
+        L = b.L
+        src = self.h_actions if actions_host is None else actions_host
+        cur = torch.cuda.current_stream(self.dev)
+        for (lo, hi), st in zip(self.bounds, self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                self.d_actions[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                io, rf = self._chunk_call(lo, hi, None)
+                sp = C.c_void_p(st.cuda_stream)
+                N.check(L.ecg_step(C.byref(b.nat), C.byref(rf), C.byref(io), hi - lo, sp), "ecg_step")
+                N.check(L.ecg_unpack(C.byref(b.nat), C.c_void_p(b.boards[lo * b.nat.board_words:].data_ptr()),
+                                     C.c_void_p(self.d_obs[lo:].data_ptr()), 1, hi - lo, sp), "ecg_unpack")
+                self.h_obs[lo:hi].copy_(self.d_obs[lo:hi], non_blocking=True)
+                self.h_reward[lo:hi].copy_(b.step_reward[lo:hi], non_blocking=True)
+                self.h_flags[lo:hi].copy_(b.flags[lo:hi], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        cur.synchronize()
+        b._mask_valid = True
+        b.step_ctr += 1
+        fl = self.h_flags
+        return self.h_obs, self.h_reward, (fl & N.FLAG_DONE) != 0, (fl & N.FLAG_WON) != 0, {}
+
+    def random_action(self) -> torch.Tensor:
+        """board.random_action() with the result copied to pinned host memory (int32 [N])"""
+        a = self.env.board.random_action(out=self.d_actions)
+        self.h_actions.copy_(a, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.h_actions
+
+
+class Match3Env:
+    """Single-environment drop-in with the reference's signature and return types (env.py:8-66):
+    numpy int64 observation, Python int reward, Python bools.  Runs the reference's own RNG semantics
+    (numpy MT19937 replay of `seed`), so episodes are bit-identical to BoardV2 driven the same way."""
+    metadata = BatchedMatch3Env.metadata
+
+    def __init__(self, width: int = 9, height: int = 9, num_types: int = 6, num_moves: int = 20, env_goal: int = 500,
+                 seed: int = None, render_mode: str = None, *, device=None, refill="replay"):
+        self._env = BatchedMatch3Env(1, width, height, num_types, num_moves, env_goal, seed, render_mode,
+                                     device=device, refill=refill, obs_dtype=torch.int64)
+        self.width, self.height, self.num_types = width, height, num_types
+        self.env_goal, self.num_moves = env_goal, num_moves
+        self.action_space = self._env.action_space
+        self.render_mode = None
+
+    class _Board:
+        def __init__(self, outer):
+            self._o = outer
+
+        @property
+        def array(self):
+            return self._o._env.board.array[0].cpu().numpy()
+
+        @property
+        def legal_actions(self):
+            return self._o._env.board.legal_actions[0]
+
+        def random_action(self) -> int:
+            return int(self._o._env.board.random_action()[0].item())
+
+    @property
+    def board(self):
+        return Match3Env._Board(self)
+
+    @property
+    def seed(self):
+        return self._env.seed
+
+    @property
+    def score(self) -> int:
+        return int(self._env.board.score[0].item())
+
+    @property
+    def moves_taken(self) -> int:
+        return int(self._env.moves_taken[0].item())
+
+    def init(self) -> np.ndarray:
+        return self.board.array
+
+    def step(self, action: int):
+        self.actions = self.board.legal_actions  # env.py:49
+        obs, reward, done, won, info = self._env.step([int(action)])
+        return obs[0].cpu().numpy(), int(reward[0].item()), bool(done[0].item()), bool(won[0].item()), info
+
+    def reset(self, seed=None):
+        obs, info = self._env.reset(seed)
+        return obs[0].cpu().numpy(), info
+
+    def render(self):
+        return None

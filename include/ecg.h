@@ -1,0 +1,145 @@
+/*
+ * ecg.h -- C-ABI of libecg.so: the B200 (sm_100a) batched stepping engine for
+ * Element-Crush-Gym's match-3 environment.
+ *
+ * The reference has no FFI: its seam is the Python `State` ABC
+ * (mctslib/abc/mcts.py:8-30) implemented by `BoardV2` (match3tile/boardv2.py:11-226),
+ * the free functions of match3tile/boardFunctions.py and `Match3Env`
+ * (match3tile/env.py:8-66).  Each entry point below names the reference code it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (e.g. torch CUDA tensors);
+ *    the library never allocates, never synchronises, and launches on `stream`
+ *    (a cudaStream_t passed as void*; NULL = the legacy default stream);
+ *  - every function returns 0 on success, <0 on a bad argument or CUDA error
+ *    (message via ecg_last_error()); data-dependent conditions are reported per
+ *    board in `status` (ECG_ST_* bits), never as errors;
+ *  - boards live in HBM in the engine's packed format (4-bit cells, bit-sliced,
+ *    32-board interleaved tiles); ecg_pack/ecg_unpack convert from
+ *    and to the reference's row-major cell arrays (BoardV2.array, int64 or uint8).
+ */
+#ifndef ECG_H
+#define ECG_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECG_VERSION 100
+
+/* per-board status bits */
+#define ECG_ST_TERMINAL 1        /* n_actions < 1: board returned unchanged (boardv2.py:44-45) */
+#define ECG_ST_STREAM_OVERFLOW 2 /* replay stream exhausted; results of this board are invalid */
+#define ECG_ST_SHUFFLE_CAP 4     /* boardv2.py:188-194 shuffle loop stopped after 64 rounds (reference: may never end) */
+#define ECG_ST_BAD_ACTION 8      /* action outside [0, action_space): no-op (reference: KeyError, boardv2.py:48) */
+#define ECG_ST_NO_LEGAL 16       /* random pick on an empty legal set: no-op (reference: ValueError in np.random.choice) */
+#define ECG_ST_BAD_CELL 32       /* ecg_pack: value outside {0, 1..min(type_mask,11), h_line, v_line, bomb, mega_token} */
+#define ECG_ST_CASCADE_CAP 64    /* cascade loop (boardv2.py:138) stopped after 1024 iterations */
+
+/* env flags written by ecg_step (env.py:54-55) */
+#define ECG_FLAG_DONE 1
+#define ECG_FLAG_WON 2
+
+#define ECG_REFILL_REPLAY 1 /* raw u32 output of numpy's legacy MT19937, restarted every step (boardv2.py:46) */
+#define ECG_REFILL_PHILOX 2 /* counter-based Philox4x32-10, keyed by (key, global board index, step) */
+
+#define ECG_TILE 32 /* boards per interleave tile */
+
+/* BoardConfig (match3tile/boardConfig.py:5-43) plus the packed-layout sizes. */
+typedef struct ecg_config {
+    int32_t rows, cols, types;
+    int32_t bits, type_mask, special_type_mask, h_line, v_line, bomb, mega_token; /* boardConfig.py:29-43 */
+    int32_t action_space; /* rows * (cols - 1) * 2, boardConfig.py:27 */
+    int32_t board_words;  /* u32 words per packed board = 4 planes x ceil(rows*(cols+1)/32) */
+    int32_t mask_words;   /* u32 words per packed legal mask = ceil(action_space/32) */
+    int32_t reserved;
+} ecg_config;
+
+/* Where refill tiles (boardv2.py:172), shuffle permutations (boardFunctions.py:16-23) and random action
+ * picks (np.random.choice, samplerTasks.py:13 / mctslib/standard/mcts.py:17) come from. */
+typedef struct ecg_refill {
+    int32_t mode;            /* ECG_REFILL_* */
+    int32_t stream_len;      /* replay: u32 words available per board */
+    const uint32_t *stream;  /* replay: raw MT19937 words (ecg_mt19937_stream) */
+    int64_t stream_stride;   /* replay: words between consecutive boards' streams; 0 = one shared stream */
+    uint32_t *stream_pos;    /* replay, optional in/out [n]: words consumed since the last reseed */
+    uint64_t philox_key;     /* philox: run key */
+    uint64_t board0;         /* philox: global index of board 0 of this call (shard offset) */
+    uint32_t step_ctr;       /* philox: step counter of this call (a rollout uses step_ctr + t) */
+    uint32_t reserved;
+} ecg_refill;
+
+/* Buffers of one lockstep step.  n-element arrays are plain board-indexed; boards/masks are packed. */
+typedef struct ecg_step_io {
+    const void *boards_in;   /* packed boards */
+    void *boards_out;        /* packed boards; may alias boards_in */
+    const int32_t *actions;  /* [n] or NULL: NULL = pick uniformly from mask_in (board.random_action()) */
+    const uint32_t *mask_in; /* packed legal mask of boards_in; required when actions == NULL */
+    int32_t *actions_out;    /* optional [n]: the action applied (-1 = none) */
+    int32_t *moves_left;     /* optional in/out [n]: BoardV2.n_actions; < 1 = terminal no-op; decremented */
+    int32_t *reward;         /* optional out [n]: points of this step (BoardV2 reward delta = env move_score) */
+    int32_t *score;          /* optional in/out [n]: cumulative reward (BoardV2._reward, env.score) */
+    int32_t *cascades;       /* optional out [n]: cascade-loop iterations of this step ("combo count") */
+    uint32_t *mask_out;      /* optional out: packed legal mask of boards_out (legal_actions of the new state) */
+    uint8_t *flags;          /* optional out [n]: ECG_FLAG_DONE | ECG_FLAG_WON (env.py:54-55); needs score+moves_left */
+    uint8_t *status;         /* optional out [n]: ECG_ST_* */
+    int32_t env_goal;        /* env.py:17 env_goal */
+    int32_t reserved;
+} ecg_step_io;
+
+int ecg_version(void);
+const char *ecg_last_error(void);
+/* kernels launched by this process so far (bench.py's gpu_launches) */
+int64_t ecg_launch_count(void);
+
+/* BoardConfig.__post_init__ (boardConfig.py:26-43).  rows == cols in 4..16, types in 1..11;
+ * shapes built into the library: 5, 6, 7, 9, 12, 16. */
+int ecg_config_init(ecg_config *cfg, int rows, int cols, int types);
+/* bytes of a packed board / mask buffer for n boards (n is rounded up to a whole tile) */
+int64_t ecg_boards_bytes(const ecg_config *cfg, int64_t n);
+int64_t ecg_masks_bytes(const ecg_config *cfg, int64_t n);
+
+/* BoardV2.array -> packed.  cells: [n, rows, cols] row-major, elem_bytes 8 (int64) or 1 (uint8).
+ * status (optional, [n]) gets ECG_ST_BAD_CELL for boards with an unrepresentable value. */
+int ecg_pack(const ecg_config *cfg, const void *cells, int elem_bytes, void *boards, uint8_t *status, int64_t n,
+             void *stream);
+/* packed -> BoardV2.array (the env's observation, env.py:56) */
+int ecg_unpack(const ecg_config *cfg, const void *boards, void *cells, int elem_bytes, int64_t n, void *stream);
+/* packed legal mask -> [n, action_space] bytes (1 = legal): membership form of BoardV2.legal_actions */
+int ecg_unpack_mask(const ecg_config *cfg, const uint32_t *mask, uint8_t *out, int64_t n, void *stream);
+
+/* raw u32 output of np.random.seed(seed) (numpy legacy MT19937 init_genrand): out[i*len + k] */
+int ecg_mt19937_stream(const uint32_t *seeds, uint32_t *out, int32_t len, int64_t n, void *stream);
+
+/* BoardV2.__init__ (boardv2.py:20-27): draw boards, redraw matched cells until no match remains.
+ * replay: consumes the board's stream from position 0; philox: substream (board, step 0xFFFFFFFF). */
+int ecg_init_boards(const ecg_config *cfg, const ecg_refill *rf, void *boards, uint8_t *status, int64_t n,
+                    void *stream);
+
+/* boardFunctions.legal_actions (:26-112) for every board, as a packed mask */
+int ecg_legal_mask(const ecg_config *cfg, const void *boards, uint32_t *mask, int64_t n, void *stream);
+
+/* np.random.choice(state.legal_actions) (samplerTasks.py:13): the idx-th legal action, ascending.
+ * replay: idx by numpy's masked rejection at stream_pos; philox: idx = mulhi(philox(0xFFFFFFFF, step, board)[0], n) */
+int ecg_random_action(const ecg_config *cfg, const ecg_refill *rf, const uint32_t *mask, int32_t *actions,
+                      uint8_t *status, int64_t n, void *stream);
+
+/* BoardV2.apply_action (boardv2.py:43-207) + Match3Env.step bookkeeping (env.py:48-56) for n boards */
+int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io, int64_t n, void *stream);
+
+/* MCTS.rollout / random_task (mctslib/standard/mcts.py:14-19, samplerTasks.py:9-14): play random legal
+ * actions until moves_left reaches 0.  boards are updated in place; total_reward[n] receives the points
+ * collected; steps_done (optional, [n]) the number of actions applied. */
+int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
+                int64_t *total_reward, int32_t *steps_done, uint8_t *status, int64_t n, void *stream);
+
+/* episode statistics (main.py:240-267 sample()): out[0]=sum(score) out[1]=n out[2]=min out[3]=max
+ * out[4]=#flags&WON out[5]=sum(score^2); out must be zero-initialised except out[2]=INT64_MAX, out[3]=INT64_MIN */
+int ecg_episode_stats(const int32_t *score, const uint8_t *flags, int64_t *out, int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -811,6 +811,7 @@ void ecgo_step_batch(const ecgo_cfg *cfg, int rng_mode, const uint32_t *raw, int
 typedef struct {
     const ecgo_cfg *cfg;
     uint64_t key, board0;
+    uint32_t step0;
     int n_moves;
     int64_t *boards, *reward, *steps;
 } pe_ctx;
@@ -820,16 +821,16 @@ static void pe_range(void *p, int64_t lo, int64_t hi) {
     const int N = c->cfg->rows * c->cfg->cols;
     for (int64_t i = lo; i < hi; i++) {
         int64_t st = 0;
-        int64_t r = ecgo_philox_episode(c->cfg, c->key, c->board0 + (uint64_t)i, c->n_moves, c->boards + i * N, &st);
+        int64_t r = ecgo_philox_episode(c->cfg, c->key, c->board0 + (uint64_t)i, c->step0, c->n_moves, c->boards + i * N, &st);
         if (c->reward) c->reward[i] = r;
         if (c->steps) c->steps[i] = st;
     }
 }
 
 /* n independent Philox lockstep episodes on all host threads (bench cpu_baseline / --impl reference) */
-void ecgo_philox_episode_batch(const ecgo_cfg *cfg, uint64_t key, uint64_t board0, int n_moves, int64_t *boards,
-                               int64_t *reward, int64_t *steps, int64_t n) {
-    pe_ctx c = {cfg, key, board0, n_moves, boards, reward, steps};
+void ecgo_philox_episode_batch(const ecgo_cfg *cfg, uint64_t key, uint64_t board0, uint32_t step0, int n_moves,
+                               int64_t *boards, int64_t *reward, int64_t *steps, int64_t n) {
+    pe_ctx c = {cfg, key, board0, step0, n_moves, boards, reward, steps};
     parallel_for(n, 16, pe_range, &c);
 }
 
@@ -888,19 +889,19 @@ int64_t ecgo_random_episode(const ecgo_cfg *cfg, uint32_t seed, int n_moves, int
 /* The engine's Philox lockstep episode: at step t the action is the
  * idx-th legal action (ascending), idx = mulhi(philox(ctr=(0xFFFFFFFF, t, board))[0], n_legal);
  * refills come from the (board, t) substream. */
-int64_t ecgo_philox_episode(const ecgo_cfg *cfg, uint64_t key, uint64_t board_index, int n_moves, int64_t *board_io,
-                            int64_t *steps) {
+int64_t ecgo_philox_episode(const ecgo_cfg *cfg, uint64_t key, uint64_t board_index, uint32_t step0, int n_moves,
+                            int64_t *board_io, int64_t *steps) {
     int64_t next[ECGO_MAX_CELLS], total = 0, nsteps = 0;
     const uint32_t k2[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
-    for (int t = 0; t < n_moves; t++) {
+    for (uint32_t t = step0; t < step0 + (uint32_t)n_moves; t++) {
         int legal[ECGO_MAX_ACTIONS];
         int k = ecgo_legal_actions(cfg, board_io, legal);
         if (k == 0) break;
-        uint32_t ctr[4] = {0xFFFFFFFFu, (uint32_t)t, (uint32_t)board_index, (uint32_t)(board_index >> 32)}, o[4];
+        uint32_t ctr[4] = {0xFFFFFFFFu, t, (uint32_t)board_index, (uint32_t)(board_index >> 32)}, o[4];
         ecgo_philox4x32_10(ctr, k2, o);
         int a = legal[(uint32_t)(((uint64_t)o[0] * (uint32_t)k) >> 32)];
         ecgo_rng rng;
-        ecgo_rng_init_philox(&rng, key, board_index, (uint32_t)t);
+        ecgo_rng_init_philox(&rng, key, board_index, t);
         int64_t r;
         ecgo_apply_action(cfg, &rng, board_io, a, next, &r, NULL, NULL);
         memcpy(board_io, next, sizeof(int64_t) * cfg->rows * cfg->cols);

@@ -206,12 +206,14 @@ class Oracle:
         self.L.ecgo_random_episode_batch(C.byref(self.cfg), _p(seeds), n_moves, _p(reward), _p(steps), C.c_int64(n))
         return reward, steps
 
-    def philox_episode_batch(self, boards, key, board0=0, n_moves=20):
-        boards = np.ascontiguousarray(boards, dtype=np.int64).copy()
+    def philox_episode_batch(self, boards, key, board0=0, n_moves=20, step0=0, inplace=False):
+        boards = np.ascontiguousarray(boards, dtype=np.int64)
+        if not inplace:
+            boards = boards.copy()
         n = boards.shape[0]
         reward = np.zeros(n, dtype=np.int64)
         steps = np.zeros(n, dtype=np.int64)
-        self.L.ecgo_philox_episode_batch(C.byref(self.cfg), C.c_uint64(key), C.c_uint64(board0), n_moves,
+        self.L.ecgo_philox_episode_batch(C.byref(self.cfg), C.c_uint64(key), C.c_uint64(board0), C.c_uint32(step0), n_moves,
                                          _p(boards), _p(reward), _p(steps), C.c_int64(n))
         return boards, reward, steps
 

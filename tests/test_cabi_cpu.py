@@ -1,0 +1,103 @@
+"""CPU-side checks of the boundary: libecg.so loads, exports every symbol include/ecg.h declares, and its
+argument checking / config arithmetic work without a GPU (no kernel is launched here)."""
+import ctypes as C
+import os
+import re
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+@pytest.fixture(scope="module")
+def E():
+    import ecg_b200
+    return ecg_b200
+
+
+def test_library_exports_every_declared_symbol(E):
+    hdr = open(os.path.join(ROOT, "include", "ecg.h")).read()
+    declared = set(re.findall(r"\b(ecg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    L = C.CDLL(E._native.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(E._native.EXPORTS), declared ^ set(E._native.EXPORTS)
+    assert E._native.lib().ecg_version() == 100
+
+
+def test_struct_layouts_match_header(E):
+    N = E._native
+    assert C.sizeof(N.Config) == 14 * 4
+    assert C.sizeof(N.Refill) == 56 and N.Refill.stream.offset == 8 and N.Refill.philox_key.offset == 32
+    assert C.sizeof(N.StepIO) == 12 * 8 + 8 and N.StepIO.env_goal.offset == 96
+
+
+def test_config_matches_reference_constants(E):
+    # SURVEY 8a row A1 [probed on the reference]
+    for (R, T), want in {(6, 4): (7, 8, 16, 24, 32, 60), (9, 6): (7, 8, 16, 24, 32, 144),
+                         (12, 7): (7, 8, 16, 24, 32, 264), (16, 8): (15, 16, 32, 48, 64, 480)}.items():
+        c = E.BoardConfig(seed=1, rows=R, columns=R, types=T)
+        assert (c.type_mask, c.h_line, c.v_line, c.bomb, c.mega_token, c.action_space) == want
+        assert c.shape == (R, R) and len(c.actions) == c.action_space
+        for a, (t1, t2) in c.actions.items():
+            assert c.encode(t1, t2) == a == c.encode(t2, t1)
+    assert E.BoardConfig(seed=0).seed != 0 and E.BoardConfig().seed  # boardConfig.py:34
+    c = E.BoardConfig(seed=1)
+    assert c.native.board_words == 12 and c.native.mask_words == 5  # 48 B boards, 20 B masks
+    with pytest.raises(Exception):
+        object.__setattr__  # frozen
+        c.rows = 3
+
+
+def test_codec_against_oracle(E):
+    from oracle.oracle import Oracle
+    for R, T in ((5, 2), (6, 4), (9, 6), (12, 7), (16, 8)):
+        c, o = E.BoardConfig(seed=1, rows=R, columns=R, types=T), Oracle(R, R, T)
+        for a in range(c.action_space):
+            assert c.decode(a) == o.decode(a)
+
+
+def test_argument_errors_are_reported_not_raised_in_c(E):
+    N = E._native
+    L = N.lib()
+    cfg = N.Config()
+    assert L.ecg_config_init(C.byref(cfg), 9, 8, 6) < 0 and b"square" in L.ecg_last_error()
+    assert L.ecg_config_init(C.byref(cfg), 10, 10, 6) < 0
+    assert L.ecg_config_init(C.byref(cfg), 9, 9, 12) < 0
+    with pytest.raises(E.EcgError):
+        E.BoardConfig(seed=1, rows=9, columns=9, types=0)
+    assert L.ecg_config_init(C.byref(cfg), 9, 9, 6) == 0
+    rf = N.Refill()
+    rf.mode = 7
+    io = N.StepIO()
+    assert L.ecg_step(C.byref(cfg), C.byref(rf), C.byref(io), 10, None) < 0
+    rf.mode = N.REFILL_PHILOX
+    assert L.ecg_step(C.byref(cfg), C.byref(rf), C.byref(io), 10, None) < 0 and b"boards_in" in L.ecg_last_error()
+    cfg.board_words = 13  # a config not made by ecg_config_init
+    assert L.ecg_legal_mask(C.byref(cfg), None, None, 1, None) < 0
+    assert L.ecg_boards_bytes(C.byref(E.BoardConfig(seed=1).native), 33) == 64 * 48
+    assert L.ecg_masks_bytes(C.byref(E.BoardConfig(seed=1).native), 33) == 64 * 20
+
+
+def test_no_cpu_fallback(E):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(E.EcgError):
+        E.BatchedBoards(E.BoardConfig(seed=1), 4)
+
+
+def test_product_package_never_uses_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import, load or link it."""
+    pkg = os.path.join(ROOT, "element-crush-gym_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|libecg_oracle|ecgo_|oracle[/\\.]oracle|hostsim", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) in ("build", "lib", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src.replace("tests/hostsim", "")), f

@@ -1,0 +1,363 @@
+"""GPU parity: the CUDA path (through the Python host layer -> ctypes -> C-ABI of libecg.so) against the CPU
+oracle and the reference-generated golden vectors.  Everything here is integer work: the bar is bit-exact.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from conftest import GOLDEN, SHAPES  # noqa: E402
+from oracle.oracle import Oracle, ST_CASCADE_CAP, ST_SHUFFLE_CAP, ST_STREAM_OVERFLOW  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+KEY = 0x1234567890ABCDEF
+
+
+@pytest.fixture(scope="module")
+def E():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ecg_b200
+    return ecg_b200
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def cfg_of(E, shape, seed=1):
+    return E.BoardConfig(seed=seed, rows=shape[0], columns=shape[1], types=shape[2])
+
+
+def np_(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_pack_unpack_roundtrip_and_bad_cells(E, shape):
+    import torch
+    o = Oracle(*shape)
+    rng = np.random.default_rng(1)
+    n = 1000 + 7  # not a multiple of the 32-board tile
+    vals = np.array(list(range(0, min(o.cfg.type_mask, 11) + 1)) + [o.cfg.h_line, o.cfg.v_line, o.cfg.bomb, o.cfg.mega_token])
+    b = vals[rng.integers(len(vals), size=(n, shape[0], shape[1]))].astype(np.int64)
+    bb = E.BatchedBoards(cfg_of(E, shape), n, arrays=b, key=KEY)
+    assert np.array_equal(np_(bb.array), b)
+    assert np.array_equal(np_(bb.observe(torch.uint8)), b.astype(np.uint8))
+    bb2 = E.BatchedBoards(cfg_of(E, shape), n, arrays=torch.as_tensor(b.astype(np.uint8)), key=KEY)
+    assert np.array_equal(np_(bb2.array), b)
+    bad = b.copy()
+    bad[5, 0, 0] = o.cfg.h_line + 1  # typed special: outside the engine's closed code set
+    with pytest.raises(ValueError):
+        E.BatchedBoards(cfg_of(E, shape), n, arrays=bad, key=KEY)
+
+
+@pytest.mark.parametrize("shape", SHAPES[:5])
+def test_legal_mask_golden(E, shape):
+    d = load("funcs_%dx%dx%d.npz" % shape)
+    o = Oracle(*shape)
+    b = d["boards"].astype(np.int64)
+    legal = np.unpackbits(d["legal"], axis=-1)[..., :o.A].astype(bool)
+    bb = E.BatchedBoards(cfg_of(E, shape), len(b), arrays=b, key=KEY)
+    assert np.array_equal(np_(bb.legal_mask()), legal)
+    assert bb.legal_actions[3] == np.flatnonzero(legal[3]).tolist()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_golden_single_steps_replay(E, shape):
+    d = load("steps_%dx%dx%d.npz" % shape)
+    n = len(d["actions"])
+    bb = E.BatchedBoards(cfg_of(E, shape), n, arrays=d["before"].astype(np.int64), refill="replay",
+                         seeds=d["seeds"].astype(np.int64), stream_len=4096)
+    bb.apply_action(d["actions"].astype(np.int32))
+    assert not np_(bb.status).any()
+    assert np.array_equal(np_(bb.array), d["after"])
+    assert np.array_equal(np_(bb.step_reward), d["rewards"])
+    assert np.array_equal(np_(bb.cascades), d["cascades"])
+    o = Oracle(*shape)
+    assert np.array_equal(np_(bb.legal_mask()), o.legal_mask_batch(d["after"].astype(np.int64)))
+
+
+def test_golden_shuffle_cases(E):
+    d = load("shuffle.npz")
+    for i in range(len(d["actions"])):
+        R, Cc, T = (int(x) for x in d["shape"][i])
+        bb = E.BatchedBoards(cfg_of(E, (R, Cc, T)), 1, arrays=d["before"][i:i + 1, :R, :Cc].astype(np.int64),
+                             refill="replay", seeds=[int(d["seeds"][i])])
+        bb.apply_action([int(d["actions"][i])])
+        assert int(bb.status[0]) == 0
+        assert np.array_equal(np_(bb.array)[0], d["after"][i, :R, :Cc])
+        assert int(bb.step_reward[0]) == d["rewards"][i] and int(bb.cascades[0]) == d["cascades"][i]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_golden_episodes_random_task(E, shape):
+    """samplerTasks.random_task (:9-14) replayed on the GPU: init boards from the MT19937 stream, picks by
+    numpy's masked rejection on the same stream, 20 steps; then the same episodes in ONE rollout kernel."""
+    d = load("episodes_%dx%dx%d.npz" % shape)
+    seeds = d["seeds"].astype(np.int64)
+    moves = int(d["moves"])
+    mk = lambda: E.BatchedBoards(cfg_of(E, shape), len(seeds), moves, refill="replay", seeds=seeds, stream_len=8192)  # noqa: E731
+    bb = mk()
+    assert np.array_equal(np_(bb.array), d["init"])
+    for t in range(moves):
+        legal = np.unpackbits(d["legal"][:, t], axis=-1)[..., :bb.cfg.action_space].astype(bool)
+        assert np.array_equal(np_(bb.legal_mask()), legal)
+        bb.apply_action(None)
+        assert np.array_equal(np_(bb.last_actions), d["actions"][:, t])
+        assert np.array_equal(np_(bb.array), d["boards"][:, t])
+        assert np.array_equal(np_(bb.step_reward), d["rewards"][:, t])
+        assert np.array_equal(np_(bb.cascades), d["cascades"][:, t])
+    assert np.array_equal(np_(bb.reward), d["rewards"].sum(axis=1))
+    assert bool(bb.is_terminal.all())
+    rb = mk()
+    total = rb.rollout()
+    assert np.array_equal(np_(total), d["rewards"].sum(axis=1))
+    assert np.array_equal(np_(rb.array), d["boards"][:, -1])
+
+
+def test_config2_4096_lockstep_boards_vs_oracle(E):
+    """BASELINE.json configs[1]: 4096 lockstep 9x9x6 boards, seeds 1..4096, random legal actions,
+    step + cascade + reward, bit-exact against the reference semantics (oracle, itself pinned to the reference)."""
+    import torch
+    n, moves = 4096, 20
+    o = Oracle(9, 9, 6)
+    seeds = np.arange(1, n + 1, dtype=np.int64)
+    env = E.BatchedMatch3Env(n, seed=1, refill="replay", stream_len=4096, obs_dtype=torch.int64)
+    assert np.array_equal(np.asarray(env.board.seeds), seeds)
+    boards = np_(env.init())
+    raw = np.stack([Oracle.mt_raw(int(s), 4096) for s in seeds])
+    score = np.zeros(n, dtype=np.int64)
+    for t in range(moves):
+        acts = np_(env.board.random_action()) if t % 2 else None  # both pick paths: separate kernel / fused
+        pos_before = np_(env.board.stream_pos).copy()
+        obs, rew, done, won, _ = env.step(acts)
+        a = np_(env.board.last_actions)
+        legal = o.legal_mask_batch(boards)
+        assert legal[np.arange(n), a].all()
+        res = o.step_batch(boards, a, mode="replay", raw=raw)
+        assert not res["status"].any() and not np_(env.board.status).any()
+        assert np.array_equal(np_(obs), res["boards"])
+        assert np.array_equal(np_(rew), res["reward"])
+        assert np.array_equal(np_(env.board.cascades), res["cascades"])
+        assert np.array_equal(np_(env.board.legal_mask()), res["legal"])
+        score += res["reward"]
+        assert np.array_equal(np_(won), score >= 500)
+        assert np.array_equal(np_(done), (score >= 500) | (t == moves - 1))
+        boards = res["boards"]
+    total, steps = o.random_episode_batch(seeds.astype(np.uint32), moves)
+    assert np.array_equal(score, total)
+    st = E.dist.stats_dict(env.board.episode_stats())
+    assert st["episodes"] == n and st["min"] == score.min() and st["max"] == score.max()
+    assert abs(st["mean"] - score.mean()) < 1e-9 and st["wins"] == int((score >= 500).sum())
+
+
+@pytest.mark.parametrize("shape", [(9, 9, 6), (6, 6, 4), (12, 12, 7), (16, 16, 8)])
+def test_philox_episodes_vs_oracle(E, shape):
+    """config 3/4 semantics at a size the oracle finishes in seconds: Philox-keyed init, picks and refills."""
+    n, moves, board0 = 8192 if shape[0] <= 9 else 2048, 20, 12345
+    o = Oracle(*shape)
+    bb = E.BatchedBoards(cfg_of(E, shape), n, moves, key=KEY, board0=board0)
+    init = np_(bb.array)
+    for i in range(8):
+        assert np.array_equal(o.init_board(o.rng_philox(KEY, board0 + i, 0xFFFFFFFF)), init[i])
+    final, total, steps = o.philox_episode_batch(init, KEY, board0, moves)
+    lock = bb.clone()
+    for t in range(moves):
+        lock.apply_action(None)
+    assert np.array_equal(np_(lock.array), final)
+    assert np.array_equal(np_(lock.reward), total)
+    roll = bb.clone()
+    tot = roll.rollout()
+    assert np.array_equal(np_(tot), total) and np.array_equal(np_(roll.array), final)
+    # sharding: the same boards stepped as two shards with their global offsets give the same result
+    half = n // 2
+    a = E.BatchedBoards(cfg_of(E, shape), half, moves, key=KEY, board0=board0)
+    b = E.BatchedBoards(cfg_of(E, shape), n - half, moves, key=KEY, board0=board0 + half)
+    ta, tb = a.rollout(), b.rollout()
+    assert np.array_equal(np.concatenate([np_(ta), np_(tb)]), total)
+    assert np.array_equal(np.concatenate([np_(a.array), np_(b.array)]), final)
+
+
+@pytest.mark.parametrize("shape", [(9, 9, 6), (6, 6, 4), (12, 12, 7), (16, 16, 8), (6, 6, 3), (5, 5, 2), (7, 7, 5),
+                                   (9, 9, 3), (9, 9, 8), (6, 6, 11)])
+def test_fuzz_dense_boards_philox(E, shape):
+    rng = np.random.default_rng(shape[0] * 100 + shape[2] + 1)
+    o = Oracle(*shape)
+    R, Cc, T = shape
+    n = 3000
+    sp = [o.cfg.h_line, o.cfg.v_line, o.cfg.bomb, o.cfg.mega_token]
+    tl = rng.integers(2, T + 1, size=n)
+    b = np.stack([rng.integers(1, t + 1, size=(R, Cc)) for t in tl]).astype(np.int64)
+    for i in range(0, n, 3):
+        for _ in range(int(rng.integers(0, 4))):
+            b[i, rng.integers(R), rng.integers(Cc)] = sp[rng.integers(4)]
+        if i % 2 == 0:
+            b[i, rng.integers(R), rng.integers(Cc)] = 0
+    lo = o.legal_mask_batch(b)
+    acts = rng.integers(0, o.A, size=n)
+    for i in range(0, n, 2):
+        la = np.flatnonzero(lo[i])
+        if len(la):
+            acts[i] = la[rng.integers(len(la))]
+    for i in range(0, n, 5):
+        (r1, c1), (r2, c2) = o.decode(int(acts[i]))
+        b[i, r1, c1] = sp[rng.integers(4)]
+        if rng.integers(2):
+            b[i, r2, c2] = sp[rng.integers(4)]
+    bb = E.BatchedBoards(cfg_of(E, shape), n, arrays=b, key=KEY, board0=77)
+    assert np.array_equal(np_(bb.legal_mask()), o.legal_mask_batch(b))
+    bb.step_ctr = 5
+    bb.apply_action(acts.astype(np.int32))
+    ro = o.step_batch(b, acts, mode="philox", key=KEY, board0=77, step_ctr=5)
+    assert np.array_equal(np_(bb.array), ro["boards"])
+    assert np.array_equal(np_(bb.step_reward), ro["reward"])
+    assert np.array_equal(np_(bb.cascades), ro["cascades"])
+    assert np.array_equal(np_(bb.status), ro["status"])
+    assert np.array_equal(np_(bb.legal_mask()), ro["legal"])
+
+
+def test_caps_flags_and_noops(E):
+    import torch
+    rng = np.random.default_rng(5)
+    o = Oracle(9, 9, 2)
+    b = rng.integers(1, 3, size=(64, 9, 9)).astype(np.int64)
+    acts = rng.integers(0, o.A, size=64)
+    bb = E.BatchedBoards(cfg_of(E, (9, 9, 2)), 64, arrays=b, key=KEY)
+    bb.apply_action(acts.astype(np.int32))
+    ro = o.step_batch(b, acts, mode="philox", key=KEY)
+    assert (np_(bb.status) & ST_CASCADE_CAP).all()
+    assert np.array_equal(np_(bb.array), ro["boards"]) and np.array_equal(np_(bb.step_reward), ro["reward"])
+    # shuffle cap on the board that hangs the reference
+    arr = np.fromfunction(lambda r, c: ((c + 2 * (r % 3)) % 6) + 1, (9, 9), dtype=np.int64).astype(np.int64)[None]
+    o = Oracle(9, 9, 6)
+    bb = E.BatchedBoards(cfg_of(E, (9, 9, 6)), 1, arrays=arr, refill="replay", seeds=[7])
+    bb.apply_action([7])
+    ro = o.step_batch(arr, [7], mode="replay", raw=Oracle.mt_raw(7, 4096))
+    assert int(bb.status[0]) & ST_SHUFFLE_CAP and ro["status"][0] & ST_SHUFFLE_CAP
+    assert np.array_equal(np_(bb.array), ro["boards"]) and int(bb.step_reward[0]) == ro["reward"][0]
+    # terminal boards and out-of-range actions are no-ops with a flag
+    b = rng.integers(1, 7, size=(4, 9, 9)).astype(np.int64)
+    bb = E.BatchedBoards(cfg_of(E, (9, 9, 6)), 4, arrays=b, key=KEY)
+    bb.moves_left.copy_(torch.tensor([0, 1, 5, 5], dtype=torch.int32))
+    bb.apply_action([3, 3, -1, 144])
+    st = np_(bb.status)
+    assert st[0] == E.ST_TERMINAL and st[2] == E.ST_BAD_ACTION and st[3] == E.ST_BAD_ACTION and st[1] == 0
+    after = np_(bb.array)
+    assert np.array_equal(after[[0, 2, 3]], b[[0, 2, 3]]) and not np_(bb.step_reward)[[0, 2, 3]].any()
+    assert np_(bb.moves_left).tolist() == [0, 0, 5, 5]
+    assert np.array_equal(np_(bb.legal_mask()), o.legal_mask_batch(after))
+    # replay stream too short
+    b = rng.integers(1, 3, size=(2, 9, 9)).astype(np.int64)
+    bb = E.BatchedBoards(cfg_of(E, (9, 9, 6)), 2, arrays=b, refill="replay", seeds=[3, 4], stream_len=2)
+    bb.apply_action([0, 1])
+    assert (np_(bb.status) & ST_STREAM_OVERFLOW).all()
+
+
+def test_mt19937_stream_kernel_matches_numpy(E):
+    d = load("rng.npz")
+    seeds = d["seeds"].astype(np.int64)
+    bb = E.BatchedBoards(cfg_of(E, (9, 9, 6)), len(seeds), refill="replay", seeds=seeds, stream_len=700)
+    got = np_(bb.stream).view(np.uint32).reshape(len(seeds), 700)
+    assert np.array_equal(got, d["raw"])
+
+
+def test_match3env_dropin_contract(E):
+    """README usage: env.reset() / env.board.random_action() / env.step(a) with reference return types."""
+    d = load("episodes_9x9x6.npz")
+    e = 4
+    seed = int(d["seeds"][e])
+    env = E.Match3Env(seed=seed)
+    obs, info = env.reset()
+    assert obs.dtype == np.int64 and obs.shape == (9, 9) and info == {}
+    assert np.array_equal(obs, d["init"][e])
+    score = 0
+    for t in range(20):
+        assert env.board.legal_actions == np.flatnonzero(np.unpackbits(d["legal"][e, t])[:144]).tolist()
+        a = int(d["actions"][e, t])
+        obs, reward, done, won, info = env.step(a)
+        assert isinstance(reward, int) and isinstance(done, bool) and isinstance(won, bool)
+        assert np.array_equal(obs, d["boards"][e, t]) and reward == d["rewards"][e, t]
+        score += reward
+        assert env.score == score and env.moves_taken == t + 1
+        assert won == (score >= 500) and done == (won or t == 19)
+    a = env.board.random_action()
+    assert a == -1 or a in env.board.legal_actions
+    obs2, _ = env.reset()
+    assert np.array_equal(obs2, d["init"][e])  # env.py:62: reset() without a seed keeps the seed
+
+
+def test_boardv2_view_matches_golden_and_state_abc(E):
+    d = load("episodes_6x6x4.npz")
+    e = 2
+    cfg = E.BoardConfig(seed=int(d["seeds"][e]), rows=6, columns=6, types=4)
+    st = E.BoardV2(int(d["moves"]), cfg)
+    assert np.array_equal(st.array, d["init"][e])
+    total = 0
+    for t in range(int(d["moves"])):
+        assert st.legal_actions == np.flatnonzero(np.unpackbits(d["legal"][e, t])[:cfg.action_space]).tolist()
+        nxt = st.apply_action(int(d["actions"][e, t]))
+        assert np.array_equal(st.array, d["init"][e] if t == 0 else d["boards"][e, t - 1])  # never mutates
+        total += int(d["rewards"][e, t])
+        assert nxt.reward == total and nxt.n_actions == st.n_actions - 1
+        assert np.array_equal(nxt.array, d["boards"][e, t])
+        st = nxt
+    assert st.is_terminal and st.apply_action(0) is st
+    c = st.clone()
+    assert c.reward == st.reward and np.array_equal(c.array, st.array)
+    with pytest.raises(KeyError):
+        E.BoardV2(3, cfg).apply_action(cfg.action_space)
+    # greedy_action: first maximum over legal actions of the one-step reward (boardv2.py:209-218)
+    s0 = E.BoardV2(5, cfg)
+    o = Oracle(6, 6, 4)
+    best, hi = None, -1
+    for a in s0.legal_actions:
+        _, r, _, _, _ = o.apply_action(o.rng_mt(cfg.seed), s0.array, a)
+        if r > hi:
+            hi, best = r, a
+    assert s0.greedy_action == best
+    bb = E.BatchedBoards(cfg, 1, 5, refill="replay", seeds=[cfg.seed])
+    assert int(bb.greedy_action()[0]) == best
+
+
+def test_full_size_properties(E):
+    """BASELINE.json configs[2] size (2^24 boards): properties that do not need the oracle at full size,
+    plus a strided sample checked against it."""
+    import torch
+    n, moves = 1 << 24, 3
+    shape = (9, 9, 6)
+    o = Oracle(*shape)
+    bb = E.BatchedBoards(cfg_of(E, shape), n, moves, key=KEY)
+    idx = torch.arange(0, n, 4099, device=bb.device)
+    before = np_(bb.array[idx])
+    acc = torch.zeros(n, dtype=torch.int64, device=bb.device)
+    sample = before
+    for t in range(moves):
+        bb.apply_action(None)
+        acc += bb.step_reward
+        obs = bb.observe(torch.uint8)
+        assert int(obs.min()) >= 1                       # refilled: no empty cell survives a step
+        assert int(obs.max()) <= 32                      # closed value set {1..6, 8, 16, 24, 32}
+        st = bb.status
+        stuck = (st & E.ST_NO_LEGAL) != 0   # a random initial board without any legal move: no-op + flag
+        assert not bool((st & ~(E.ST_NO_LEGAL | E.ST_SHUFFLE_CAP)).any())
+        assert int(stuck.sum()) < n // 10000
+        assert int(bb.cascades[~stuck].min()) >= 1 and int(bb.step_reward.min()) >= 0
+        a = np_(bb.last_actions[idx])
+        res = o.step_batch(sample, a, mode="philox", key=KEY, board0=0, step_ctr=t)
+        # board0 + i with i the *sample* index differs from the global index: check each sampled board on its own
+        for j, g in enumerate(np_(idx)[:64]):
+            r1 = o.step_batch(sample[j:j + 1], a[j:j + 1], mode="philox", key=KEY, board0=int(g), step_ctr=t)
+            assert np.array_equal(r1["boards"][0], np_(bb.array[idx[j]:idx[j] + 1])[0])
+            assert r1["reward"][0] == int(bb.step_reward[idx[j]])
+        sample = np_(bb.array[idx])
+        del res
+    assert torch.equal(acc, bb.reward)                   # score is the sum of the step rewards
+    assert bool((bb.is_terminal | ((bb.status & E.ST_NO_LEGAL) != 0)).all())
+    # a stable board has no run of three: stepping the legal mask kernel twice is idempotent
+    m1 = bb.packed_mask().clone()
+    bb._mask_valid = False
+    assert torch.equal(m1, bb.packed_mask())
