@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libecg.so")
+# ECG_LIB selects another build of the same library (e.g. the -DECG_PROFILE_PHASES one used for ncu)
+LIB_PATH = os.environ.get("ECG_LIB") or os.path.join(_HERE, "lib", "libecg.so")
 
 ST_TERMINAL, ST_STREAM_OVERFLOW, ST_SHUFFLE_CAP, ST_BAD_ACTION = 1, 2, 4, 8
 ST_NO_LEGAL, ST_BAD_CELL, ST_CASCADE_CAP = 16, 32, 64

@@ -22,6 +22,13 @@
 #define ECG_HD_NOINLINE __attribute__((noinline))
 #endif
 
+// -DECG_PROFILE_PHASES keeps the major phases out of line so ncu attributes instructions per phase
+#if defined(ECG_PROFILE_PHASES)
+#define ECG_PHASE ECG_HD_NOINLINE
+#else
+#define ECG_PHASE ECG_HD
+#endif
+
 namespace ecg {
 
 ECG_HD int popc32(uint32_t x) {

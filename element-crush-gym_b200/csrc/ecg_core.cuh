@@ -54,11 +54,17 @@ ECG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 }
 
 // Throughput mode: bounded ints by multiply-high of one u32 (no rejection).
+// Draw addressing inside the (board, step) substream (engine-defined; mirrored by the oracle's Philox mode):
+//   cascade iteration j (0-based): refill draws are words j*2048 + d, d = rank of the hole in ROW-MAJOR
+//   order (tiles are i.i.d., so the order is free; row-major = bit order makes the loop convergent);
+//   shuffle draws of that iteration start at word j*2048 + 1024.
 struct PhiloxRng {
+    static constexpr bool ROW_MAJOR = true;
     uint32_t k0, k1, b0, b1, step;
     uint32_t pos;
     uint32_t blk[4];
     uint32_t blk_idx;
+    uint32_t dig_x, dig_left; // digit(): up to 4 base-n digits are taken from one word
     bool overflow;
     ECG_HD void init(uint64_t key, uint64_t board, uint32_t step_) {
         k0 = (uint32_t)key;
@@ -69,9 +75,14 @@ struct PhiloxRng {
         pos = 0;
         blk_idx = 0xFFFFFFFFu;
         blk[0] = blk[1] = blk[2] = blk[3] = 0u;
+        dig_x = dig_left = 0u;
         overflow = false;
     }
     ECG_HD void reseed() {} // counter-based: one substream per (board, step), never restarted
+    ECG_HD void seek(uint32_t p) {
+        pos = p;
+        dig_left = 0u;
+    }
     ECG_HD uint32_t u32() {
         const uint32_t k = pos++;
         const uint32_t b = k >> 2;
@@ -83,6 +94,18 @@ struct PhiloxRng {
         return j == 0 ? blk[0] : j == 1 ? blk[1] : j == 2 ? blk[2] : blk[3];
     }
     ECG_HD uint32_t below(uint32_t n) { return n <= 1u ? 0u : mulhi32(u32(), n); }
+    // Refill tiles: successive base-n digits of the fraction word / 2^32 (digit = hi32(x * n), x = lo32(x * n)),
+    // 4 per word.  Each digit is uniform up to n^4 / 2^32 (3e-7 for 6 types).
+    ECG_HD uint32_t digit(uint32_t n) {
+        if (dig_left == 0u) {
+            dig_x = u32();
+            dig_left = 4u;
+        }
+        dig_left--;
+        const uint32_t v = mulhi32(dig_x, n);
+        dig_x *= n;
+        return v;
+    }
 };
 
 // The action pick of a Philox lockstep step: idx = mulhi(philox(ctr=(0xFFFFFFFF, step, board))[0], n)
@@ -96,6 +119,7 @@ ECG_HD uint32_t philox_pick(uint64_t key, uint64_t board, uint32_t step, uint32_
 // restarts it at the top of every apply_action, boardv2.py:46, and in shuffle, boardFunctions.py:17)
 // with numpy's masked-rejection bounded integers (RandomState.randint / random_interval).
 struct ReplayRng {
+    static constexpr bool ROW_MAJOR = false; // the reference's order: columns left to right, top cell first
     const uint32_t *raw;
     uint32_t len, pos;
     bool overflow;
@@ -106,6 +130,7 @@ struct ReplayRng {
         overflow = false;
     }
     ECG_HD void reseed() { pos = 0; }
+    ECG_HD void seek(uint32_t) {} // strictly sequential like the reference
     ECG_HD uint32_t u32() {
         const uint32_t k = pos++;
         if (k >= len) {
@@ -128,6 +153,7 @@ struct ReplayRng {
             if (v <= rng || overflow) return v <= rng ? v : 0u;
         }
     }
+    ECG_HD uint32_t digit(uint32_t n) { return below(n); } // np.random.randint(1, types + 1) per tile
 };
 
 // ------------------------------------------------------------------ board
@@ -155,7 +181,7 @@ struct Derived { // views of a board used by match / legal logic
 };
 
 template <class SH>
-ECG_HD Derived<typename SH::G> derive(const Board<typename SH::G> &b) {
+ECG_PHASE Derived<typename SH::G> derive(const Board<typename SH::G> &b) {
     using G = typename SH::G;
     Derived<G> d;
     d.spec = b.p[3] & b.p[2];
@@ -373,7 +399,7 @@ ECG_HD_NOINLINE void scan_order_matches(Matches<typename SH::G> &m, const BB<SH:
 
 // get_matches + get_match_spawn_mask of the token board (boardFunctions.py:121-169).
 template <class SH>
-ECG_HD void find_matches(const Derived<typename SH::G> &d, Matches<typename SH::G> &m) {
+ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename SH::G> &m) {
     using G = typename SH::G;
     constexpr int W = G::W, S = G::S;
     m.A = eq_at<SH, 1>(d);
@@ -413,7 +439,7 @@ ECG_HD void find_matches(const Derived<typename SH::G> &d, Matches<typename SH::
 // the tokens differ (:103) and a moved token completes a run of three with two equal tokens
 // that are not its swap partner (:41-61, :74-94).  A/D must be eq-right/eq-down of this board.
 template <class SH>
-ECG_HD void legal_swaps(const Derived<typename SH::G> &d, const BB<SH::G::W> &A, const BB<SH::G::W> &D,
+ECG_PHASE void legal_swaps(const Derived<typename SH::G> &d, const BB<SH::G::W> &A, const BB<SH::G::W> &D,
                         BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
     using G = typename SH::G;
     constexpr int W = G::W, S = G::S;
@@ -453,7 +479,7 @@ ECG_HD void legal_swaps(const Derived<typename SH::G> &d, const BB<SH::G::W> &A,
 // swap bitboards -> action-ordered mask, action = r*(2C-1) + c (horizontal) | + (C-1) + c (vertical)
 // (boardConfig.py:45-69)
 template <class G>
-ECG_HD void swaps_to_actions(const BB<G::W> &HL, const BB<G::W> &VL, uint32_t out[G::AW]) {
+ECG_PHASE void swaps_to_actions(const BB<G::W> &HL, const BB<G::W> &VL, uint32_t out[G::AW]) {
 #pragma unroll
     for (int i = 0; i < G::AW; i++) out[i] = 0u;
 #pragma unroll
@@ -552,7 +578,7 @@ ECG_HD_NOINLINE BB<SH::G::W> trigger_specials(const Board<typename SH::G> &bd, B
 
 // gravity (boardv2.py:166-173): every column keeps its non-empty cells, in order, at the bottom
 template <class G>
-ECG_HD void gravity(Board<G> &b) {
+ECG_PHASE void gravity(Board<G> &b) {
     constexpr int W = G::W, S = G::S;
     for (;;) {
         const BB<W> occ = b.p[0] | b.p[1] | b.p[2] | b.p[3];
@@ -569,18 +595,35 @@ ECG_HD void gravity(Board<G> &b) {
     }
 }
 
-// refill (boardv2.py:172-173): columns left to right, first draw = topmost hole
-template <class G, class RNG>
-ECG_HD void refill(Board<G> &b, RNG &rng, uint32_t types) {
+// refill (boardv2.py:172-173).  Replay: the reference's order (columns left to right, first draw =
+// topmost hole).  Philox: holes in bit (row-major) order, draws addressed per cascade iteration.
+template <class SH, class RNG>
+ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int iter) {
+    using G = typename SH::G;
     const BB<G::W> holes = andn(G::valid(), b.p[0] | b.p[1] | b.p[2] | b.p[3]);
-    uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
-    while (cols) {
-        int bit = ctz32(cols);
-        cols &= cols - 1u;
-        do {
-            set_code(b, bit, 1 + (int)rng.below(types));
-            bit += G::S;
-        } while (bit < G::NB && testbit(holes, bit));
+    if constexpr (RNG::ROW_MAJOR) {
+        rng.seek((uint32_t)iter * 2048u);
+#pragma unroll
+        for (int w = 0; w < G::W; w++) {
+            uint32_t h = holes.w[w];
+            while (h) {
+                const uint32_t bit = h & (0u - h);
+                h ^= bit;
+                const uint32_t v = 1u + rng.digit(types);
+#pragma unroll
+                for (int k = 0; k < SH::TPL; k++) b.p[k].w[w] |= (0u - ((v >> k) & 1u)) & bit;
+            }
+        }
+    } else {
+        uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
+        while (cols) {
+            int bit = ctz32(cols);
+            cols &= cols - 1u;
+            do {
+                set_code(b, bit, 1 + (int)rng.digit(types));
+                bit += G::S;
+            } while (bit < G::NB && testbit(holes, bit));
+        }
     }
 }
 
@@ -624,18 +667,27 @@ struct StepOut {
     uint32_t status;  // ST_* bits
 };
 
-// BoardV2.apply_action (boardv2.py:43-207) minus the terminal test.  On return `bd` is the next
-// board, `HL`/`VL` its legal swaps (the reference computes legal_actions on the final board too,
-// :188, to decide about shuffling).
-template <class SH, class RNG>
-ECG_HD void step_board(Board<typename SH::G> &bd, int action, uint32_t types, RNG &rng, StepOut &out,
-                       BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+// One in-flight BoardV2.apply_action (boardv2.py:43-207), cut at the cascade-loop boundary so a kernel
+// can interleave boards: step_begin = swap + special-pair branch / first get_matches (:46-136),
+// step_iter = ONE iteration of the cascade loop (:138-202).  The GPU step kernel keeps one Lane per
+// thread and lets threads whose cascade ended fetch the next board while others keep cascading.
+template <class SH>
+struct Lane {
+    Board<typename SH::G> bd;
+    BB<SH::G::W> cleared;       // plain cells whose token_board entry was zeroed (match mask / special region)
+    BB<SH::G::W> sp, sk0, sk1;  // pending spawns (get_match_spawn_mask) of the coming iteration
+    int reward, cascades;
+    uint32_t status;
+};
+
+template <class SH>
+ECG_HD void step_begin(Lane<SH> &L, int action) {
     using G = typename SH::G;
     constexpr int W = G::W;
-    out.reward = 0;
-    out.cascades = 0;
-    out.status = 0;
-    rng.reseed(); // :46
+    Board<G> &bd = L.bd;
+    L.reward = 0;
+    L.cascades = 0;
+    L.status = 0;
     int b1, b2;
     decode_action<G>(action, b1, b2); // source, target (:48)
     { // swap (:51)
@@ -646,82 +698,116 @@ ECG_HD void step_board(Board<typename SH::G> &bd, int action, uint32_t types, RN
             if (x != y) bd.p[k] = bd.p[k] ^ both;
         }
     }
-    Derived<G> d = derive<SH>(bd);
-    Matches<G> m;
-    BB<W> cleared; // plain cells whose token_board entry was zeroed
     const int c1 = cell_code<G>(bd, b1), c2 = cell_code<G>(bd, b2);
     const int s1 = c1 >= 12 ? c1 - 11 : 0, s2 = c2 >= 12 ? c2 - 11 : 0; // 0 none, 1 h, 2 v, 3 bomb, 4 mega
-    bool matched = false;
+    bool matched = true;
+    L.sp = bb_zero<W>();
+    L.sk0 = bb_zero<W>();
+    L.sk1 = bb_zero<W>();
+    L.cleared = bb_zero<W>();
     if (s1 | s2) {
         const int tr = b2 / G::S, tc = b2 - tr * G::S; // target (:112-132 are relative to the target cell)
         const int lo = s1 < s2 ? s1 : s2, hi = s1 < s2 ? s2 : s1;
-        m.sp = bb_zero<W>();
-        m.sk0 = bb_zero<W>();
-        m.sk1 = bb_zero<W>();
-        cleared = bb_zero<W>();
+        matched = false;
         if (hi == 4) { // a mega token is involved
-            if (lo == 4) cleared = G::valid(); // :81-82
+            if (lo == 4) L.cleared = G::valid(); // :81-82
             // mega + bomb / line / plain (:84-103): token = max(token1, token2) is the mega value itself,
             // never present in token_board -> no cell changes and get_matches is skipped
         } else if (lo == 3 && hi == 3) { // bomb + bomb (:112-116)
-            cleared = G::rows(tr - 2, tr + 2) & G::cols(tc - 2, tc + 2);
+            L.cleared = G::rows(tr - 2, tr + 2) & G::cols(tc - 2, tc + 2);
         } else if (hi == 3 && lo >= 1) { // bomb + line (:123-125)
-            cleared = G::cols(tc - 2, tc + 2) | G::rows(tr - 2, tr + 2);
+            L.cleared = G::cols(tc - 2, tc + 2) | G::rows(tr - 2, tr + 2);
         } else if (lo == 1 && hi == 2) { // h_line + v_line (:130-132): ROW slices [:tc] and [tr:]
-            cleared = G::rows(0, tc) | G::rows(tr, G::R);
+            L.cleared = G::rows(0, tc) | G::rows(tr, G::R);
         } else { // one special + plain, or two equal lines (:134-136)
             matched = true;
         }
-    } else {
-        matched = true;
     }
     if (matched) {
+        const Derived<G> d = derive<SH>(bd);
+        Matches<G> m;
         find_matches<SH>(d, m);
-        cleared = m.mask;
+        L.cleared = m.mask;
+        L.sp = m.sp;
+        L.sk0 = m.sk0;
+        L.sk1 = m.sk1;
     }
-    for (;;) { // :138
-        out.cascades++;
-        BB<W> z = cleared | d.spec | andn(G::valid(), d.nz | d.spec); // token_board == 0
-        if (any(d.spec)) z |= trigger_specials<SH>(bd, d.spec);
-        { // points (:58-65, :157-158)
-            const BB<W> k1 = bd.p[1] & d.spec, k0 = bd.p[0] & d.spec;
-            out.reward += 2 * popcount(andn(z, d.spec)) + 25 * popcount(andn(d.spec, k1)) +
-                          50 * popcount(andn(k1, k0)) + 250 * popcount(k1 & k0);
-        }
-        // :161-163 clear, add spawns (always onto cleared cells), clip
+}
+
+// One cascade iteration.  Returns true when the step is over; then HL/VL are the legal swaps of the
+// final board (the reference computes legal_actions there too, :188, to decide about shuffling).
+template <class SH, class RNG>
+ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    using G = typename SH::G;
+    constexpr int W = G::W;
+    Board<G> &bd = L.bd;
+    L.cascades++;
+    { // :141-163 trigger pass, points, clear, spawn, clip
+        const BB<W> spec = bd.p[3] & bd.p[2];
+        const BB<W> occ = bd.p[0] | bd.p[1] | bd.p[2] | bd.p[3];
+        BB<W> z = L.cleared | spec | andn(G::valid(), occ); // token_board == 0
+        if (any(spec)) z |= trigger_specials<SH>(bd, spec);
+        const BB<W> k1 = bd.p[1] & spec, k0 = bd.p[0] & spec; // points (:58-65, :157-158)
+        L.reward += 2 * popcount(andn(z, spec)) + 25 * popcount(andn(spec, k1)) + 50 * popcount(andn(k1, k0)) +
+                    250 * popcount(k1 & k0);
 #pragma unroll
         for (int k = 0; k < 4; k++) bd.p[k] = andn(bd.p[k], z);
-        bd.p[3] |= m.sp;
-        bd.p[2] |= m.sp;
-        bd.p[0] |= m.sk0;
-        bd.p[1] |= m.sk1;
-        gravity<G>(bd);          // :166-170
-        refill<G>(bd, rng, types); // :172-173
-        d = derive<SH>(bd);
-        find_matches<SH>(d, m);  // :181
-        if (!m.found) {
-            legal_swaps<SH>(d, m.A, m.D, HL, VL);
-            int shuffles = 0;
-            while (!m.found && !any(HL | VL)) { // :188-194
-                if (shuffles++ >= SHUFFLE_CAP) {
-                    out.status |= ST_SHUFFLE_CAP;
-                    break;
-                }
-                shuffle_rows<SH>(bd, rng);
-                d = derive<SH>(bd);
-                find_matches<SH>(d, m);
-                if (!m.found) legal_swaps<SH>(d, m.A, m.D, HL, VL);
+        bd.p[3] |= L.sp; // spawns always land on cleared cells
+        bd.p[2] |= L.sp;
+        bd.p[0] |= L.sk0;
+        bd.p[1] |= L.sk1;
+    }
+    gravity<G>(bd);                             // :166-170
+    refill<SH>(bd, rng, types, L.cascades - 1); // :172-173
+    Derived<G> d = derive<SH>(bd);
+    Matches<G> m;
+    find_matches<SH>(d, m); // :181
+    bool done = false;
+    if (!m.found) {
+        legal_swaps<SH>(d, m.A, m.D, HL, VL);
+        int shuffles = 0;
+        while (!m.found && !any(HL | VL)) { // :188-194
+            if (shuffles++ >= SHUFFLE_CAP) {
+                L.status |= ST_SHUFFLE_CAP;
+                break;
             }
-            if (!m.found) break; // :195
+            if (shuffles == 1) rng.seek((uint32_t)(L.cascades - 1) * 2048u + 1024u);
+            shuffle_rows<SH>(bd, rng);
+            d = derive<SH>(bd);
+            find_matches<SH>(d, m);
+            if (!m.found) legal_swaps<SH>(d, m.A, m.D, HL, VL);
         }
-        cleared = m.mask; // :199
-        if (rng.overflow || out.cascades >= CASCADE_CAP) {
-            if (!rng.overflow) out.status |= ST_CASCADE_CAP;
+        done = !m.found; // :195
+    }
+    if (!done) {
+        L.cleared = m.mask; // :199
+        L.sp = m.sp;        // :202
+        L.sk0 = m.sk0;
+        L.sk1 = m.sk1;
+        if (rng.overflow || L.cascades >= CASCADE_CAP) {
+            if (!rng.overflow) L.status |= ST_CASCADE_CAP;
             legal_swaps<SH>(d, m.A, m.D, HL, VL);
-            break;
+            done = true;
         }
     }
-    if (rng.overflow) out.status |= ST_STREAM_OVERFLOW;
+    if (done && rng.overflow) L.status |= ST_STREAM_OVERFLOW;
+    return done;
+}
+
+// BoardV2.apply_action (boardv2.py:43-207) minus the terminal test, run to completion.
+template <class SH, class RNG>
+ECG_HD void step_board(Board<typename SH::G> &bd, int action, uint32_t types, RNG &rng, StepOut &out,
+                       BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    Lane<SH> L;
+    L.bd = bd;
+    rng.reseed(); // :46
+    step_begin<SH>(L, action);
+    while (!step_iter<SH>(L, rng, types, HL, VL)) {
+    }
+    bd = L.bd;
+    out.reward = L.reward;
+    out.cascades = L.cascades;
+    out.status = L.status;
 }
 
 // BoardV2.__init__ (boardv2.py:20-27): draw a board, redraw matched cells until clean.

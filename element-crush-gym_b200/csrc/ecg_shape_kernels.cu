@@ -208,49 +208,25 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards,
 }
 
 
-template <class SH, bool PHILOX>
-__global__ void __launch_bounds__(BLOCK) step_kernel(RefillDev rf, StepDev io, long long n) {
-    using G = typename SH::G;
-    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= n) return;
-    Board<G> b;
-    load_board<G>(io.boards_in, i, b);
-    int moves = io.moves_left ? io.moves_left[i] : 1;
-    typename RngOf<PHILOX>::type rng;
-    if constexpr (PHILOX) rng.init(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr);
-    else rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
+// ---- the lockstep step: a persistent warp loop over work chunks ------------------------------------
+//
+// Cascade lengths differ per board (mean 1.5 iterations, long tail), so "one thread = one board for the
+// whole launch" leaves most lanes idle while the slowest board of the warp finishes.  Instead every lane
+// runs a small state machine: FETCH a board (load, choose the action, swap, first match pass), then one
+// cascade ITERATION per trip of the warp loop, then FINISH (legal mask, stores) and fetch the next board
+// in the same trip.  Every trip therefore runs one cascade iteration on (almost) all 32 lanes.
+// Boards are handed out in chunks of CHUNK consecutive boards; warp w owns chunks w, w + nwarps, ...
+// (static, no atomics); lanes that ask in the same trip receive consecutive boards, so their 16-byte
+// chunk loads/stores stay contiguous inside the 32-board tile.
+constexpr int CHUNK = 256;
 
-    StepOut so = {0, 0, 0};
-    int action = -1;
-    if (moves < 1) { // boardv2.py:44
-        so.status = ST_TERMINAL;
-    } else if (io.actions) {
-        action = io.actions[i];
-        if (action < 0 || action >= G::A) {
-            so.status = ST_BAD_ACTION;
-            action = -1;
-        }
-    } else { // board.random_action(): uniform over the legal set of the current board
-        uint32_t m[G::AW];
-        load_mask<G>(io.mask_in, i, m);
-        const int cnt = mask_count<G>(m);
-        if (cnt == 0) {
-            so.status = ST_NO_LEGAL;
-        } else {
-            uint32_t idx;
-            if constexpr (PHILOX) idx = philox_pick(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr, (uint32_t)cnt);
-            else idx = rng.below((uint32_t)cnt);
-            action = mask_select<G>(m, (int)idx);
-        }
-    }
-    BB<G::W> HL, VL;
-    if (action >= 0) {
-        step_board<SH>(b, action, (uint32_t)io.types, rng, so, HL, VL);
-        moves -= 1;
-    } else if (io.mask_out) {
-        legal_of<SH>(b, HL, VL);
-    }
-    if (action >= 0 || io.boards_out != io.boards_in) store_board<G>(io.boards_out, i, b);
+template <class SH, bool PHILOX>
+__device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev &io, long long i,
+                                             const Board<typename SH::G> &b, bool stepped, int action, int moves,
+                                             int reward, int cascades, uint32_t status, const BB<SH::G::W> &HL,
+                                             const BB<SH::G::W> &VL, uint32_t rpos) {
+    using G = typename SH::G;
+    if (stepped || io.boards_out != io.boards_in) store_board<G>(io.boards_out, i, b);
     if (io.mask_out) {
         uint32_t m[G::AW];
         swaps_to_actions<G>(HL, VL, m);
@@ -258,20 +234,133 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(RefillDev rf, StepDev io, l
     }
     if (io.actions_out) io.actions_out[i] = action;
     if (io.moves_left) io.moves_left[i] = moves;
-    if (io.reward) io.reward[i] = so.reward;
-    int score = so.reward;
+    if (io.reward) io.reward[i] = reward;
+    int score = reward;
     if (io.score) {
         score += io.score[i];
         io.score[i] = score;
     }
-    if (io.cascades) io.cascades[i] = so.cascades;
+    if (io.cascades) io.cascades[i] = cascades;
     if (io.flags) { // env.py:54-55
         const bool won = score >= io.env_goal;
         io.flags[i] = (uint8_t)((won || moves == 0 ? ECG_FLAG_DONE : 0) | (won ? ECG_FLAG_WON : 0));
     }
-    if (io.status) io.status[i] = (uint8_t)so.status;
+    if (io.status) io.status[i] = (uint8_t)status;
     if constexpr (!PHILOX)
-        if (rf.stream_pos) rf.stream_pos[i] = rng.pos;
+        if (rf.stream_pos) rf.stream_pos[i] = rpos;
+}
+
+template <class SH, bool PHILOX>
+__global__ void __launch_bounds__(BLOCK) step_kernel(RefillDev rf, StepDev io, long long n) {
+    using G = typename SH::G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    const long long stride = (((long long)gridDim.x * BLOCK) >> 5) * CHUNK;
+    // warp-uniform cursor over this warp's chunks
+    long long chunk0 = warp * CHUNK;
+    long long next = chunk0 < n ? chunk0 : n;
+    long long end = chunk0 + CHUNK < n ? chunk0 + CHUNK : n;
+    if (chunk0 >= n) end = n;
+
+    Lane<SH> L;
+    long long idx = 0;
+    int moves = 0, action = -1;
+    uint32_t rpos = 0; // replay: words consumed since the last reseed
+    bool active = false;
+    BB<G::W> HL, VL;
+
+    for (;;) {
+        // ---- FETCH: idle lanes take the next boards of the cursor
+        const unsigned need = __ballot_sync(FULL, !active);
+        if (need) {
+            const int rank = __popc(need & ((1u << lane) - 1u));
+            const int cnt = __popc(need);
+            const long long avail = end - next;
+            long long cand;
+            if (rank < avail) {
+                cand = next + rank;
+            } else { // the request spills into this warp's next chunk
+                const long long c2 = chunk0 + stride;
+                const long long e2 = c2 + CHUNK < n ? c2 + CHUNK : n;
+                cand = c2 + (rank - avail);
+                if (cand >= e2) cand = n;
+            }
+            if (cnt >= avail) {
+                chunk0 += stride;
+                if (chunk0 >= n) {
+                    next = end = n;
+                } else {
+                    end = chunk0 + CHUNK < n ? chunk0 + CHUNK : n;
+                    next = chunk0 + (cnt - avail);
+                    if (next > end) next = end;
+                }
+            } else {
+                next += cnt;
+            }
+            if (!active && cand < n) {
+                idx = cand;
+                load_board<G>(io.boards_in, idx, L.bd);
+                moves = io.moves_left ? io.moves_left[idx] : 1;
+                uint32_t st = 0;
+                action = -1;
+                rpos = 0;
+                if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[idx] : 0u;
+                if (moves < 1) { // boardv2.py:44
+                    st = ST_TERMINAL;
+                } else if (io.actions) {
+                    action = io.actions[idx];
+                    if (action < 0 || action >= G::A) {
+                        st = ST_BAD_ACTION;
+                        action = -1;
+                    }
+                } else { // board.random_action(): uniform over the legal set of the current board
+                    uint32_t m[G::AW];
+                    load_mask<G>(io.mask_in, idx, m);
+                    const int c = mask_count<G>(m);
+                    if (c == 0) {
+                        st = ST_NO_LEGAL;
+                    } else {
+                        uint32_t k;
+                        if constexpr (PHILOX) {
+                            k = philox_pick(rf.key, rf.board0 + (unsigned long long)idx, rf.step_ctr, (uint32_t)c);
+                        } else {
+                            ReplayRng rng;
+                            rng.init(rf.stream + idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+                            k = rng.below((uint32_t)c);
+                            rpos = rng.pos;
+                            if (rng.overflow) st = ST_STREAM_OVERFLOW;
+                        }
+                        action = mask_select<G>(m, (int)k);
+                    }
+                }
+                if (action >= 0) {
+                    rpos = 0; // np.random.seed(cfg.seed) at the top of apply_action (boardv2.py:46)
+                    step_begin<SH>(L, action);
+                    L.status |= st;
+                    moves -= 1;
+                    active = true;
+                } else { // no-op boards are finished on the spot
+                    if (io.mask_out) legal_of<SH>(L.bd, HL, VL);
+                    finish_board<SH, PHILOX>(rf, io, idx, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos);
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        // ---- ITERATE: one cascade iteration on every active lane; FINISH the boards whose cascade ended
+        if (active) {
+            typename RngOf<PHILOX>::type rng;
+            if constexpr (PHILOX) rng.init(rf.key, rf.board0 + (unsigned long long)idx, rf.step_ctr);
+            else rng.init(rf.stream + idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+            const bool fin = step_iter<SH>(L, rng, (uint32_t)io.types, HL, VL);
+            if constexpr (!PHILOX) rpos = rng.pos;
+            if (fin) {
+                finish_board<SH, PHILOX>(rf, io, idx, L.bd, true, action, moves, L.reward, L.cascades, L.status, HL, VL,
+                                         rpos);
+                active = false;
+            }
+        }
+    }
 }
 
 template <class SH, bool PHILOX>
@@ -378,14 +467,29 @@ void op_random_action(bool philox, RefillDev rf, const uint32_t *mask, int32_t *
     if (philox) random_action_kernel<SHN, true><<<g, BLOCK, 0, s>>>(rf, mask, actions, status, n);
     else random_action_kernel<SHN, false><<<g, BLOCK, 0, s>>>(rf, mask, actions, status, n);
 }
+// persistent grid: all resident warps, but no more than there are chunks
+template <class K>
+unsigned persistent_grid(K kernel, long long n) {
+    static int resident = 0; // per kernel instantiation
+    if (resident == 0) {
+        int dev = 0, sms = 148, per_sm = 4;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const long long chunks = (n + CHUNK - 1) / CHUNK;
+    const long long blocks = (chunks + (BLOCK / 32) - 1) / (BLOCK / 32);
+    return (unsigned)(blocks < resident ? blocks : resident);
+}
+
 void op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
-    const unsigned g = grid_for(n, BLOCK);
     if (wide) {
-        if (philox) step_kernel<SHW, true><<<g, BLOCK, 0, s>>>(rf, io, n);
-        else step_kernel<SHW, false><<<g, BLOCK, 0, s>>>(rf, io, n);
+        if (philox) step_kernel<SHW, true><<<persistent_grid(step_kernel<SHW, true>, n), BLOCK, 0, s>>>(rf, io, n);
+        else step_kernel<SHW, false><<<persistent_grid(step_kernel<SHW, false>, n), BLOCK, 0, s>>>(rf, io, n);
     } else {
-        if (philox) step_kernel<SHN, true><<<g, BLOCK, 0, s>>>(rf, io, n);
-        else step_kernel<SHN, false><<<g, BLOCK, 0, s>>>(rf, io, n);
+        if (philox) step_kernel<SHN, true><<<persistent_grid(step_kernel<SHN, true>, n), BLOCK, 0, s>>>(rf, io, n);
+        else step_kernel<SHN, false><<<persistent_grid(step_kernel<SHN, false>, n), BLOCK, 0, s>>>(rf, io, n);
     }
 }
 void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left, long long *total_reward,

@@ -197,6 +197,28 @@ uint32_t ecgo_rng_below(ecgo_rng *r, uint32_t n) {
     }
 }
 
+/* Philox mode only: jump inside the (board, step) substream (see PhiloxRng in the engine's ecg_core.cuh) */
+void ecgo_rng_seek(ecgo_rng *r, int64_t pos) {
+    if (r->mode == 2) {
+        r->pos = pos;
+        r->dig_left = 0;
+    }
+}
+
+/* One refill tile minus 1.  Modes 0/1: np.random.randint(1, types+1) == 1 + below(types).  Mode 2 (engine
+ * defined): successive base-n digits of word / 2^32, four per word (uniform up to n^4 / 2^32). */
+uint32_t ecgo_rng_digit(ecgo_rng *r, uint32_t n) {
+    if (r->mode != 2) return ecgo_rng_below(r, n);
+    if (r->dig_left == 0) {
+        r->dig_x = ecgo_rng_u32(r);
+        r->dig_left = 4;
+    }
+    r->dig_left--;
+    uint64_t p = (uint64_t)r->dig_x * n;
+    r->dig_x = (uint32_t)p;
+    return (uint32_t)(p >> 32);
+}
+
 void ecgo_mt_raw(uint32_t seed, uint32_t *out, int64_t n) {
     ecgo_rng r;
     ecgo_rng_init_mt(&r, seed);
@@ -625,18 +647,38 @@ int ecgo_apply_action(const ecgo_cfg *cfg, ecgo_rng *rng, const int64_t *in, int
             if (token_spawn[i] != 0) next_state[i] += token_spawn[i];
         for (int i = 0; i < N; i++) next_state[i] = next_state[i] < 0 ? 0 : (next_state[i] > 32 ? 32 : next_state[i]);
         /* :166-173 gravity + refill, columns left to right, first draw = topmost cell */
-        for (int col = 0; col < W; col++) {
-            int64_t tokens[ECGO_MAX_DIM];
-            int nt = 0;
-            for (int r = 0; r < H; r++)
-                if (next_state[r * W + col] > 0) tokens[nt++] = next_state[r * W + col];
-            if (nt == H) continue;
-            int k = H - nt;
-            for (int r = 0; r < k; r++) {
-                next_state[r * W + col] = 1 + ecgo_rng_below(rng, (uint32_t)cfg->types);
-                draws++;
+        if (rng->mode != 2) {
+            for (int col = 0; col < W; col++) {
+                int64_t tokens[ECGO_MAX_DIM];
+                int nt = 0;
+                for (int r = 0; r < H; r++)
+                    if (next_state[r * W + col] > 0) tokens[nt++] = next_state[r * W + col];
+                if (nt == H) continue;
+                int k = H - nt;
+                for (int r = 0; r < k; r++) {
+                    next_state[r * W + col] = 1 + ecgo_rng_digit(rng, (uint32_t)cfg->types);
+                    draws++;
+                }
+                for (int r = 0; r < nt; r++) next_state[(k + r) * W + col] = tokens[r];
             }
-            for (int r = 0; r < nt; r++) next_state[(k + r) * W + col] = tokens[r];
+        } else {
+            /* Philox mode (engine-defined addressing): same gravity; the i.i.d. tiles are assigned to the
+             * holes in row-major order from words (iteration * 2048 + d) of the (board, step) substream */
+            for (int col = 0; col < W; col++) {
+                int64_t tokens[ECGO_MAX_DIM];
+                int nt = 0;
+                for (int r = 0; r < H; r++)
+                    if (next_state[r * W + col] > 0) tokens[nt++] = next_state[r * W + col];
+                int k = H - nt;
+                for (int r = 0; r < k; r++) next_state[r * W + col] = 0;
+                for (int r = 0; r < nt; r++) next_state[(k + r) * W + col] = tokens[r];
+            }
+            ecgo_rng_seek(rng, (int64_t)(cascades - 1) * 2048);
+            for (int i = 0; i < N; i++)
+                if (next_state[i] == 0) {
+                    next_state[i] = 1 + ecgo_rng_digit(rng, (uint32_t)cfg->types);
+                    draws++;
+                }
         }
         REBUILD_SUB_BOARDS(); /* :176-178 */
         g.n_groups = 0;
@@ -651,6 +693,7 @@ int ecgo_apply_action(const ecgo_cfg *cfg, ecgo_rng *rng, const int64_t *in, int
                 status |= ECGO_ST_SHUFFLE_CAP;
                 break;
             }
+            if (shuffles == 1) ecgo_rng_seek(rng, (int64_t)(cascades - 1) * 2048 + 1024);
             ecgo_shuffle(cfg, rng, next_state);
             REBUILD_SUB_BOARDS();
             g.n_groups = 0;

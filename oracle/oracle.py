@@ -32,7 +32,7 @@ class Rng(C.Structure):
         ("mode", C.c_int), ("seed", C.c_uint32), ("mt", C.c_uint32 * 624), ("mti", C.c_int),
         ("raw", C.c_void_p), ("raw_len", C.c_int64), ("key", C.c_uint32 * 2), ("board", C.c_uint32 * 2),
         ("step", C.c_uint32), ("blk", C.c_uint32 * 4), ("blk_idx", C.c_int64), ("pos", C.c_int64),
-        ("overflow", C.c_int),
+        ("overflow", C.c_int), ("dig_x", C.c_uint32), ("dig_left", C.c_uint32),
     ]
 
 
