@@ -170,7 +170,7 @@ int ecg_config_init(ecg_config *cfg, int rows, int cols, int types) {
     cfg->mega_token = cfg->type_mask + cfg->special_type_mask + 1;
     cfg->action_space = rows * (cols - 1) * 2;
     cfg->board_words = 4 * ((rows * (cols + 1) + 31) / 32);
-    cfg->mask_words = (cfg->action_space + 31) / 32;
+    cfg->mask_words = cfg->board_words / 2; /* two swap bitboards (horizontal, vertical) */
     return 0;
 }
 
@@ -249,6 +249,7 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
     if (!io->actions && !io->mask_in) return fail("ecg_step: actions == NULL needs mask_in (random legal action)");
     if (io->flags && !(io->score && io->moves_left)) return fail("ecg_step: flags need score and moves_left");
     if (n <= 0) return 0;
+    if (n > (1ll << 30)) return fail("ecg_step: at most 2^30 boards per call");
     StepDev sd;
     sd.boards_in = io->boards_in;
     sd.boards_out = io->boards_out;

@@ -55,8 +55,10 @@ ECG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 
 // Throughput mode: bounded ints by multiply-high of one u32 (no rejection).
 // Draw addressing inside the (board, step) substream (engine-defined; mirrored by the oracle's Philox mode):
-//   cascade iteration j (0-based): refill draws are words j*2048 + d, d = rank of the hole in ROW-MAJOR
-//   order (tiles are i.i.d., so the order is free; row-major = bit order makes the loop convergent);
+//   word 0: the random action pick of this step (philox_pick);
+//   cascade iteration j (0-based): refill tiles come from words j*2048 + 1, + 2, ...: four base-n digits per
+//   word, handed to the holes in ROW-MAJOR order (tiles are i.i.d., so the order is free; row-major = bit
+//   order makes the loop convergent);
 //   shuffle draws of that iteration start at word j*2048 + 1024.
 struct PhiloxRng {
     static constexpr bool ROW_MAJOR = true;
@@ -83,6 +85,14 @@ struct PhiloxRng {
         pos = p;
         dig_left = 0u;
     }
+    // hand over a block computed earlier (the step kernel computes one block per trip for all lanes)
+    ECG_HD void preset_block(uint32_t index, const uint32_t w[4]) {
+        blk[0] = w[0];
+        blk[1] = w[1];
+        blk[2] = w[2];
+        blk[3] = w[3];
+        blk_idx = index;
+    }
     ECG_HD uint32_t u32() {
         const uint32_t k = pos++;
         const uint32_t b = k >> 2;
@@ -108,11 +118,15 @@ struct PhiloxRng {
     }
 };
 
-// The action pick of a Philox lockstep step: idx = mulhi(philox(ctr=(0xFFFFFFFF, step, board))[0], n)
+// The action pick of a Philox lockstep step: idx = mulhi(word 0 of the (board, step) substream, n).
+// blk receives block 0, whose words 1..3 are the first refill words of the step (cached by the step kernel).
+ECG_HD uint32_t philox_pick(uint64_t key, uint64_t board, uint32_t step, uint32_t n, uint32_t blk[4]) {
+    philox4x32_10(0u, step, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)key, (uint32_t)(key >> 32), blk);
+    return n <= 1u ? 0u : mulhi32(blk[0], n);
+}
 ECG_HD uint32_t philox_pick(uint64_t key, uint64_t board, uint32_t step, uint32_t n) {
-    uint32_t o[4];
-    philox4x32_10(0xFFFFFFFFu, step, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)key, (uint32_t)(key >> 32), o);
-    return n <= 1u ? 0u : mulhi32(o[0], n);
+    uint32_t blk[4];
+    return philox_pick(key, board, step, n, blk);
 }
 
 // Parity mode: replays the raw u32 output of numpy's legacy MT19937 (np.random.seed(cfg.seed)
@@ -221,6 +235,15 @@ ECG_HD void add_spawn(Matches<typename SH::G> &m, const BB<SH::G::W> &cells, int
     if (kind & 2) m.sk1 |= cells;
 }
 
+// spawns of groups whose centres cannot coincide (disjoint groups): plain OR
+template <class SH>
+ECG_HD void add_spawn_disjoint(Matches<typename SH::G> &m, const BB<SH::G::W> &cells, int kind) {
+    if (SH::CLIP && kind >= K_BOMB) kind = K_VLINE;
+    m.sp |= cells;
+    if (kind & 1) m.sk0 |= cells;
+    if (kind & 2) m.sk1 |= cells;
+}
+
 template <class G>
 ECG_HD int run_right(const BB<G::W> &A, int b) { // cells in the A-chain starting at b (>= 1)
     return 1 + ctz32(~extract32(A, b));
@@ -242,12 +265,12 @@ ECG_HD_NOINLINE void mega_spawns(Matches<typename SH::G> &m, BB<SH::G::W> L5h, B
     while (any(L5h)) {
         const int b = pop_lowest(L5h);
         const int n = run_right<G>(m.A, b);
-        add_spawn<SH>(m, onehot<G::W>(b + n / 2), K_MEGA); // sorted(group)[len // 2], boardFunctions.py:13
+        add_spawn_disjoint<SH>(m, onehot<G::W>(b + n / 2), K_MEGA); // sorted(group)[len // 2], boardFunctions.py:13
     }
     while (any(L5v)) {
         const int b = pop_lowest(L5v);
         const int n = run_down<G>(m.D, b);
-        add_spawn<SH>(m, onehot<G::W>(b + (n / 2) * G::S), K_MEGA);
+        add_spawn_disjoint<SH>(m, onehot<G::W>(b + (n / 2) * G::S), K_MEGA);
     }
 }
 
@@ -262,7 +285,7 @@ ECG_HD_NOINLINE void corner_spawns(Matches<typename SH::G> &m, BB<SH::G::W> K) {
         const int idx = (hl + vl) / 2; // >= 3
         // sorted multiset: (r,c),(r,c),(r,c+1)..(r,c+hl-1),(r+1,c)..(r+vl-1,c)
         const int centre = idx <= hl ? b + idx - 1 : b + (idx - hl) * G::S;
-        add_spawn<SH>(m, onehot<G::W>(centre), K_BOMB);
+        add_spawn_disjoint<SH>(m, onehot<G::W>(centre), K_BOMB);
     }
 }
 
@@ -284,8 +307,10 @@ ECG_HD_NOINLINE void merged_spawns(Matches<typename SH::G> &m, const BB<SH::G::W
         const int hl = testbit(HO, b) ? run_right<G>(m.A, b) : 0;
         const int vl = testbit(VO, b) ? run_down<G>(m.D, b) : 0;
         int gid = nm;
-        for (int x = 1; x < hl; x++) { // crossing cells of the H part: covered by an earlier vertical run
-            if (!testbit(VC, b + x)) continue;
+        uint32_t cross = hl ? (extract32(VC, b) & ((1u << hl) - 1u)) : 0u; // H cells covered by an earlier vertical run
+        while (cross) {
+            const int x = ctz32(cross);
+            cross &= cross - 1u;
             for (int j = 0; j < nm; j++) {
                 const int ob = rec[j] & 511, ovl = (rec[j] >> 14) & 31, og = (int)(rec[j] >> 19);
                 const int orow = ob / G::S, ocol = ob - orow * G::S;
@@ -307,17 +332,18 @@ ECG_HD_NOINLINE void merged_spawns(Matches<typename SH::G> &m, const BB<SH::G::W
             }
             members++;
             n += hl + vl;
-            for (int x = 0; x < hl; x++) {
-                const BB<W> cell = onehot<W>(b + x);
-                thrice |= twice & cell;
-                twice |= once & cell;
-                once |= cell;
+            if (hl) { // the horizontal run is a contiguous bit range
+                const BB<W> run = bitrange<W>(b, b + hl);
+                thrice |= twice & run;
+                twice |= once & run;
+                once |= run;
             }
-            for (int y = 0; y < vl; y++) {
-                const BB<W> cell = onehot<W>(b + y * G::S);
-                thrice |= twice & cell;
-                twice |= once & cell;
-                once |= cell;
+            if (vl) { // the vertical run: one column, rows r .. r+vl-1
+                const int r = b / G::S, c = b - r * G::S;
+                const BB<W> run = shl_rt(G::col0(), c) & bitrange<W>(r * G::S, (r + vl) * G::S);
+                thrice |= twice & run;
+                twice |= once & run;
+                once |= run;
             }
         }
         if (n <= 3) continue; // boardFunctions.py:161
@@ -325,17 +351,29 @@ ECG_HD_NOINLINE void merged_spawns(Matches<typename SH::G> &m, const BB<SH::G::W
         if (members == 1 && vl0 == 0) kind = n > 4 ? K_MEGA : K_VLINE;      // one row   (:163-164)
         else if (members == 1 && hl0 == 0) kind = n > 4 ? K_MEGA : K_HLINE; // one column (:165-166)
         else kind = K_BOMB;                                                  // (:168)
-        // centre = sorted(group)[n // 2] with duplicates (:8-13)
+        // centre = sorted(group)[n // 2] with duplicates (:8-13): skip whole words by popcount, then walk
         int idx = n / 2, centre = 0;
-        BB<W> walk = once;
-        while (any(walk)) {
-            const int b = pop_lowest(walk);
-            const int mult = 1 + (testbit(twice, b) ? 1 : 0) + (testbit(thrice, b) ? 1 : 0);
-            if (idx < mult) {
-                centre = b;
-                break;
+        bool found = false;
+#pragma unroll
+        for (int wi = 0; wi < W; wi++) {
+            if (found) continue;
+            const int cw = popc32(once.w[wi]) + popc32(twice.w[wi]) + popc32(thrice.w[wi]);
+            if (idx >= cw) {
+                idx -= cw;
+                continue;
             }
-            idx -= mult;
+            uint32_t o = once.w[wi];
+            while (o) {
+                const uint32_t bit = o & (0u - o);
+                o ^= bit;
+                const int mult = 1 + ((twice.w[wi] & bit) ? 1 : 0) + ((thrice.w[wi] & bit) ? 1 : 0);
+                if (idx < mult) {
+                    centre = 32 * wi + ctz32(bit);
+                    found = true;
+                    break;
+                }
+                idx -= mult;
+            }
         }
         add_spawn<SH>(m, onehot<W>(centre), kind);
     }
@@ -354,7 +392,7 @@ ECG_HD_NOINLINE void scan_order_matches(Matches<typename SH::G> &m, const BB<SH:
     constexpr uint32_t RM = (1u << G::C) - 1u;
     BB<W> HF = bb_zero<W>(), HO = bb_zero<W>(), VO = bb_zero<W>(), VC = bb_zero<W>();
     uint32_t vcov = 0;
-    for (int r = 0; r < G::R; r++) {
+    for (int r = 0; r < G::R; r++) { // rolled on purpose: rare path, keep the instruction footprint small
         const int b0 = r * G::S;
         const uint32_t hs_r = extract32(hs, b0) & RM, A_r = extract32(m.A, b0) & RM;
         const uint32_t vs_r = extract32(vs, b0) & RM, D_r = extract32(m.D, b0) & RM;
@@ -391,10 +429,94 @@ ECG_HD_NOINLINE void scan_order_matches(Matches<typename SH::G> &m, const BB<SH:
     const BB<W> HOs = andn(HO, K), VOs = andn(VO, K);
     const BB<W> L4h = HOs & shr<2>(m.A), L4v = VOs & shr<2 * G::S>(m.D);
     const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * G::S>(m.D);
-    add_spawn<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);        // horizontal 4-run -> v_line (:164)
-    add_spawn<SH>(m, shl<2 * G::S>(andn(L4v, L5v)), K_HLINE); // vertical 4-run -> h_line (:166)
+    add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);        // horizontal 4-run -> v_line (:164)
+    add_spawn_disjoint<SH>(m, shl<2 * G::S>(andn(L4v, L5v)), K_HLINE); // vertical 4-run -> h_line (:166)
     if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
     if (any(K)) corner_spawns<SH>(m, K);
+}
+
+// One straight run as its own group (boardFunctions.py:161-166): start bit, length, step (1 = horizontal)
+template <class SH>
+ECG_HD void straight_spawn(Matches<typename SH::G> &m, int start, int n, int step) {
+    if (n <= 3) return;
+    const int kind = n > 4 ? K_MEGA : (step == 1 ? K_VLINE : K_HLINE);
+    add_spawn_disjoint<SH>(m, onehot<SH::G::W>(start + (n / 2) * step), kind);
+}
+
+// Exactly ONE cell x belongs to both a horizontal and a vertical run (L, T and + shapes): the outcome of
+// the reference's scan has a closed form.  H = [s, e] in row r, V = [t, b] in
+// column c, x = (r, c); every other run of the board is disjoint from both and forms its own group.
+//   t < r, c > s : V fires first from (t, c) and covers x; H fires from s and crosses it -> ONE merged group,
+//                  x listed twice -> bomb at the median of the sorted multiset.
+//   t < r, c == s: x is covered, so H can only fire from s + 1: its own group [s+1, e] if it still has 3 cells,
+//                  else the two cells right of x stay on the board.
+//   t == r, c == s: the origin fires both runs (corner): one group, origin listed twice -> bomb.
+//   t == r, c > s : H fires from s and consumes x, so V can only start one row lower: its own group
+//                  [r+1, b] if it still has 3 cells, else the two cells below x stay.
+template <class SH>
+ECG_HD_NOINLINE void single_cross_matches(Matches<typename SH::G> &m, const BB<SH::G::W> &hs, const BB<SH::G::W> &vs,
+                                          const BB<SH::G::W> &HV3, int x) {
+    using G = typename SH::G;
+    constexpr int W = G::W, S = G::S;
+    const int r = x / S, c = x - r * S;
+    const uint32_t Ar = extract32(m.A, r * S) & ((1u << G::C) - 1u);
+    const int e = c + ctz32(~(Ar >> c));
+    int s = c;
+    while (s > 0 && ((Ar >> (s - 1)) & 1u)) s--;
+    int t = r, b = r;
+    while (t > 0 && testbit(m.D, (t - 1) * S + c)) t--;
+    while (testbit(m.D, b * S + c)) b++;
+    const int hl = e - s + 1, vl = b - t + 1;
+    const BB<W> Hm = bitrange<W>(r * S + s, r * S + e + 1);
+    const BB<W> Vm = shl_rt(G::col0(), c) & bitrange<W>(t * S, (b + 1) * S);
+    // all other runs: disjoint maximal runs, one group each (same formulas as the intersection-free case)
+    m.mask = andn(HV3, Hm | Vm);
+    const BB<W> L4h = andn(andn(hs, shl<1>(m.A)) & shr<2>(m.A), Hm);
+    const BB<W> L4v = andn(andn(vs, shl<S>(m.D)) & shr<2 * S>(m.D), Vm);
+    if (any(L4h | L4v)) {
+        const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
+        add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
+        add_spawn_disjoint<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
+        if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
+    }
+    // groups are created in scan order; the pair's groups may be created between the others', but spawn
+    // centres of disjoint groups never coincide, so the order of the add_spawn calls is irrelevant here
+    if (t < r) {
+        if (c != s) { // merged T / + shape
+            m.mask |= Hm | Vm;
+            const int a = r - t; // vertical cells above row r
+            int idx = (hl + vl) / 2, centre;
+            if (idx < a) {
+                centre = (t + idx) * S + c;
+            } else if (idx - a < hl + 1) { // row r holds s..c, c, c+1..e
+                idx -= a;
+                centre = r * S + (idx <= c - s ? s + idx : s + idx - 1);
+            } else {
+                centre = (r + 1 + (idx - a - (hl + 1))) * S + c;
+            }
+            add_spawn_disjoint<SH>(m, onehot<W>(centre), K_BOMB);
+        } else {
+            m.mask |= Vm;
+            straight_spawn<SH>(m, t * S + c, vl, S);
+            if (hl >= 4) {
+                m.mask |= Hm;
+                straight_spawn<SH>(m, r * S + s + 1, hl - 1, 1);
+            }
+        }
+    } else {
+        if (c == s) { // corner at the origin: (r,c),(r,c),(r,c+1)..(r,e),(r+1,c)..(b,c)
+            m.mask |= Hm | Vm;
+            const int idx = (hl + vl) / 2;
+            add_spawn_disjoint<SH>(m, onehot<W>(idx <= hl ? x + idx - 1 : x + (idx - hl) * S), K_BOMB);
+        } else {
+            m.mask |= Hm;
+            straight_spawn<SH>(m, r * S + s, hl, 1);
+            if (vl >= 4) {
+                m.mask |= Vm;
+                straight_spawn<SH>(m, (r + 1) * S + c, vl - 1, S);
+            }
+        }
+    }
 }
 
 // get_matches + get_match_spawn_mask of the token board (boardFunctions.py:121-169).
@@ -416,8 +538,14 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
     }
     const BB<W> H3 = hs | shl<1>(hs) | shl<2>(hs);
     const BB<W> V3 = vs | shl<S>(vs) | shl<2 * S>(vs);
-    if (any(H3 & V3)) { // intersecting runs: the reference's result depends on scan order
-        scan_order_matches<SH>(m, hs, vs);
+    const BB<W> X = H3 & V3;
+    if (any(X)) { // intersecting runs: the reference's result depends on scan order
+        if (popcount(X) == 1) {
+            BB<W> x1 = X;
+            single_cross_matches<SH>(m, hs, vs, H3 | V3, pop_lowest(x1));
+        } else {
+            scan_order_matches<SH>(m, hs, vs);
+        }
         return;
     }
     // disjoint straight runs: every maximal run is one group
@@ -426,8 +554,8 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
     const BB<W> L4v = andn(vs, shl<S>(m.D)) & shr<2 * S>(m.D);
     if (any(L4h | L4v)) {
         const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
-        add_spawn<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
-        add_spawn<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
+        add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
+        add_spawn_disjoint<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
         if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
     }
 }
@@ -523,8 +651,61 @@ ECG_HD int mask_select(const uint32_t m[G::AW], int k) {
             }
         }
     }
-    for (int j = 0; j < k; j++) w &= w - 1u;
-    return base + ctz32(w | 0x80000000u);
+    // k-th set bit of w by bisection on popcounts (no data-dependent loop)
+    int pos = 0, c;
+    c = popc32(w & 0xFFFFu);
+    if (k >= c) { k -= c; pos += 16; w >>= 16; }
+    c = popc32(w & 0xFFu);
+    if (k >= c) { k -= c; pos += 8; w >>= 8; }
+    c = popc32(w & 0xFu);
+    if (k >= c) { k -= c; pos += 4; w >>= 4; }
+    c = popc32(w & 0x3u);
+    if (k >= c) { k -= c; pos += 2; w >>= 2; }
+    if (k >= (int)(w & 1u)) pos += 1;
+    return base + pos;
+}
+
+// The legal set in "swap-bitboard order": all horizontal swaps by (row, col), then all vertical swaps by
+// (row, col).  This is the order of the packed legal mask in HBM (HL words, then VL words) and of the
+// Philox-mode random pick; the reference's ascending-action order is produced by swaps_to_actions.
+template <class G>
+ECG_HD int swaps_count(const BB<G::W> &HL, const BB<G::W> &VL) {
+    return popcount(HL) + popcount(VL);
+}
+template <class G>
+ECG_HD int swaps_select(const BB<G::W> &HL, const BB<G::W> &VL, int k) { // k-th legal swap -> action id
+    uint32_t w = 0;
+    int base = 0;
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < 2 * G::W; i++) {
+        const uint32_t x = i < G::W ? HL.w[i < G::W ? i : 0] : VL.w[i < G::W ? 0 : i - G::W];
+        const int c = popc32(x);
+        if (!done) {
+            if (k < c) {
+                w = x;
+                base = 32 * i;
+                done = true;
+            } else {
+                k -= c;
+            }
+        }
+    }
+    int pos = 0, c;
+    c = popc32(w & 0xFFFFu);
+    if (k >= c) { k -= c; pos += 16; w >>= 16; }
+    c = popc32(w & 0xFFu);
+    if (k >= c) { k -= c; pos += 8; w >>= 8; }
+    c = popc32(w & 0xFu);
+    if (k >= c) { k -= c; pos += 4; w >>= 4; }
+    c = popc32(w & 0x3u);
+    if (k >= c) { k -= c; pos += 2; w >>= 2; }
+    if (k >= (int)(w & 1u)) pos += 1;
+    int bit = base + pos;
+    const bool vertical = bit >= 32 * G::W;
+    if (vertical) bit -= 32 * G::W;
+    const int r = bit / G::S, col = bit - r * G::S;
+    return r * G::ROWA + col + (vertical ? G::C - 1 : 0);
 }
 
 // ------------------------------------------------------------------ step
@@ -559,19 +740,65 @@ ECG_HD void set_code(Board<G> &b, int bit, int code) { // cell must be empty
 }
 
 // effects of every special token on the board (boardv2.py:141-154): all of them fire in every
-// cascade iteration because a typeless special always has token_board == 0.
+// cascade iteration because a typeless special always has token_board == 0.  Specials are on some
+// board of the warp in almost every trip, so lines are expanded bit-parallel, without a per-token loop.
+template <class G>
+ECG_HD BB<G::W> fill_rows_with_any(const BB<G::W> &x) { // every row holding a bit of x, completely
+    // per row field (C cells + pad bit): x + (2^C - 1) carries into the pad bit iff the row is non-empty
+    constexpr int W = G::W;
+    const BB<W> v = G::valid(), pad = shl<G::C>(G::col0());
+    BB<W> sum;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint64_t t = (uint64_t)x.w[i] + v.w[i] + carry;
+        sum.w[i] = (uint32_t)t;
+        carry = (uint32_t)(t >> 32);
+    }
+    const BB<W> flag = shr<G::C>(sum & pad); // bit r*S set for non-empty rows
+    // flag * (2^C - 1) = (flag << C) - flag: no borrow leaves a row field
+    const BB<W> hi = shl<G::C>(flag);
+    BB<W> r;
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint64_t t = (uint64_t)hi.w[i] - flag.w[i] - borrow;
+        r.w[i] = (uint32_t)t;
+        borrow = (uint32_t)(t >> 63);
+    }
+    return r;
+}
+template <class G>
+ECG_HD BB<G::W> fill_cols_with_any(const BB<G::W> &x) { // every column holding a bit of x, completely
+    constexpr int S = G::S;
+    BB<G::W> u = x | shr<S>(x); // fold all rows onto row 0 ...
+    u |= shr<2 * S>(u);
+    if (G::R > 4) u |= shr<4 * S>(u);
+    if (G::R > 8) u |= shr<8 * S>(u);
+    u = u & G::template rect<0, 1, 0, G::C>();
+    u |= shl<S>(u); // ... and broadcast row 0 back down
+    u |= shl<2 * S>(u);
+    if (G::R > 4) u |= shl<4 * S>(u);
+    if (G::R > 8) u |= shl<8 * S>(u);
+    return u & G::valid();
+}
 template <class SH>
-ECG_HD_NOINLINE BB<SH::G::W> trigger_specials(const Board<typename SH::G> &bd, BB<SH::G::W> spec) {
+ECG_HD BB<SH::G::W> trigger_specials(const Board<typename SH::G> &bd, const BB<SH::G::W> &spec) {
     using G = typename SH::G;
-    BB<G::W> z = bb_zero<G::W>();
-    while (any(spec)) {
-        const int b = pop_lowest(spec);
+    constexpr int W = G::W;
+    const BB<W> k0 = bd.p[0] & spec, k1 = bd.p[1] & spec;
+    BB<W> z = fill_rows_with_any<G>(andn(andn(spec, k0), k1)); // h_line: its row (:147-148)
+    const BB<W> vl = andn(k0, k1);
+    if (any(vl)) z |= fill_cols_with_any<G>(vl);               // v_line: its column (:149-150)
+    BB<W> bombs = andn(k1, k0);
+    while (any(bombs)) { // bomb at (i, j): token_board[j-1:j+1, i-1:i+1] -- transposed 2x2; a negative start
+        const int b = pop_lowest(bombs); // (i == 0 or j == 0) makes the Python slice empty (:151-154)
         const int i = b / G::S, j = b - i * G::S;
-        const int kind = (testbit(bd.p[0], b) ? 1 : 0) | (testbit(bd.p[1], b) ? 2 : 0);
-        if (kind == K_HLINE) z |= G::rows(i, i + 1);
-        else if (kind == K_VLINE) z |= G::cols(j, j + 1);
-        else if (kind == K_BOMB && i > 0 && j > 0) // token_board[j-1:j+1, i-1:i+1] (transposed; a negative start empties the slice)
-            z |= G::rows(j - 1, j + 1) & G::cols(i - 1, i + 1);
+        if (i > 0 && j > 0) {
+            const int t = (j - 1) * G::S + (i - 1); // cells t, t+1, t+S, t+S+1
+            const BB<W> two = onehot<W>(t) | onehot<W>(t + 1);
+            z |= (two | shl<G::S>(two)) & G::valid();
+        }
     }
     return z;
 }
@@ -602,7 +829,7 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
     using G = typename SH::G;
     const BB<G::W> holes = andn(G::valid(), b.p[0] | b.p[1] | b.p[2] | b.p[3]);
     if constexpr (RNG::ROW_MAJOR) {
-        rng.seek((uint32_t)iter * 2048u);
+        rng.seek((uint32_t)iter * 2048u + 1u);
 #pragma unroll
         for (int w = 0; w < G::W; w++) {
             uint32_t h = holes.w[w];
@@ -610,8 +837,11 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
                 const uint32_t bit = h & (0u - h);
                 h ^= bit;
                 const uint32_t v = 1u + rng.digit(types);
-#pragma unroll
-                for (int k = 0; k < SH::TPL; k++) b.p[k].w[w] |= (0u - ((v >> k) & 1u)) & bit;
+                // the cell is empty, so adding the bit is OR-ing it (IMAD keeps the logic pipe free)
+                b.p[0].w[w] += bit * (v & 1u);
+                b.p[1].w[w] += bit * ((v >> 1) & 1u);
+                b.p[2].w[w] += bit * ((v >> 2) & 1u);
+                if (SH::TPL > 3) b.p[3].w[w] += bit * (v >> 3);
             }
         }
     } else {
@@ -667,6 +897,31 @@ struct StepOut {
     uint32_t status;  // ST_* bits
 };
 
+// Swapping two special tokens (boardv2.py:81-132).  s1/s2: 0 none, 1 h_line, 2 v_line, 3 bomb, 4 mega of
+// the source / target cell after the swap; `target` is the bit of the second (lower/right) cell, all regions
+// are relative to it.  Returns true when the normal get_matches path applies (:134-136).
+template <class G>
+ECG_HD_NOINLINE bool special_pair(int s1, int s2, int target, BB<G::W> &cleared) {
+    const int tr = target / G::S, tc = target - tr * G::S;
+    const int lo = s1 < s2 ? s1 : s2, hi = s1 < s2 ? s2 : s1;
+    if (hi == 4) { // a mega token is involved
+        if (lo == 4) cleared = G::valid(); // :81-82
+        // mega + bomb / line / plain (:84-103): token = max(token1, token2) is the mega value itself, never
+        // present in token_board -> no cell changes and get_matches is skipped
+        return false;
+    }
+    if (hi == 3 && lo >= 1) { // bomb + bomb: 4x4 block (:112-116); bomb + line: 4 columns and 4 rows (:123-125)
+        const BB<G::W> rr = G::rows(tr - 2, tr + 2), cc = G::cols(tc - 2, tc + 2);
+        cleared = lo == 3 ? (rr & cc) : (rr | cc);
+        return false;
+    }
+    if (lo == 1 && hi == 2) { // h_line + v_line (:130-132): ROW slices [:tc] and [tr:]
+        cleared = andn(G::valid(), G::rows(tc, tr));
+        return false;
+    }
+    return true; // one special + plain, or two equal lines
+}
+
 // One in-flight BoardV2.apply_action (boardv2.py:43-207), cut at the cascade-loop boundary so a kernel
 // can interleave boards: step_begin = swap + special-pair branch / first get_matches (:46-136),
 // step_iter = ONE iteration of the cascade loop (:138-202).  The GPU step kernel keeps one Lane per
@@ -705,24 +960,7 @@ ECG_HD void step_begin(Lane<SH> &L, int action) {
     L.sk0 = bb_zero<W>();
     L.sk1 = bb_zero<W>();
     L.cleared = bb_zero<W>();
-    if (s1 | s2) {
-        const int tr = b2 / G::S, tc = b2 - tr * G::S; // target (:112-132 are relative to the target cell)
-        const int lo = s1 < s2 ? s1 : s2, hi = s1 < s2 ? s2 : s1;
-        matched = false;
-        if (hi == 4) { // a mega token is involved
-            if (lo == 4) L.cleared = G::valid(); // :81-82
-            // mega + bomb / line / plain (:84-103): token = max(token1, token2) is the mega value itself,
-            // never present in token_board -> no cell changes and get_matches is skipped
-        } else if (lo == 3 && hi == 3) { // bomb + bomb (:112-116)
-            L.cleared = G::rows(tr - 2, tr + 2) & G::cols(tc - 2, tc + 2);
-        } else if (hi == 3 && lo >= 1) { // bomb + line (:123-125)
-            L.cleared = G::cols(tc - 2, tc + 2) | G::rows(tr - 2, tr + 2);
-        } else if (lo == 1 && hi == 2) { // h_line + v_line (:130-132): ROW slices [:tc] and [tr:]
-            L.cleared = G::rows(0, tc) | G::rows(tr, G::R);
-        } else { // one special + plain, or two equal lines (:134-136)
-            matched = true;
-        }
-    }
+    if (s1 | s2) matched = special_pair<G>(s1, s2, b2, L.cleared);
     if (matched) {
         const Derived<G> d = derive<SH>(bd);
         Matches<G> m;

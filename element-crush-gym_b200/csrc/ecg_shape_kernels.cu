@@ -29,7 +29,10 @@ static_assert(ECG_ST_TERMINAL == ST_TERMINAL && ECG_ST_STREAM_OVERFLOW == ST_STR
 
 namespace {
 
-constexpr int BLOCK = 128;
+#ifndef ECG_BLOCK
+#define ECG_BLOCK 128
+#endif
+constexpr int BLOCK = ECG_BLOCK;
 
 
 // ------------------------------------------------------------------ packed I/O
@@ -66,17 +69,22 @@ __device__ __forceinline__ void store_board(void *boards, long long i, const Boa
     for (int k = 0; k < CH; k++) __stcs(base + k * 32, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
 }
 
+// packed legal mask = the two swap bitboards, HL words then VL words, tiled like the boards with 4-byte words
 template <class G>
-__device__ __forceinline__ void load_mask(const uint32_t *mask, long long i, uint32_t m[G::AW]) {
-    const uint32_t *base = mask + (i >> 5) * (G::AW * 32) + (i & 31);
+__device__ __forceinline__ void load_mask(const uint32_t *mask, long long i, BB<G::W> &HL, BB<G::W> &VL) {
+    const uint32_t *base = mask + (i >> 5) * (2 * G::W * 32) + (i & 31);
 #pragma unroll
-    for (int k = 0; k < G::AW; k++) m[k] = __ldcs(base + k * 32);
+    for (int k = 0; k < G::W; k++) HL.w[k] = __ldcs(base + k * 32);
+#pragma unroll
+    for (int k = 0; k < G::W; k++) VL.w[k] = __ldcs(base + (G::W + k) * 32);
 }
 template <class G>
-__device__ __forceinline__ void store_mask(uint32_t *mask, long long i, const uint32_t m[G::AW]) {
-    uint32_t *base = mask + (i >> 5) * (G::AW * 32) + (i & 31);
+__device__ __forceinline__ void store_mask(uint32_t *mask, long long i, const BB<G::W> &HL, const BB<G::W> &VL) {
+    uint32_t *base = mask + (i >> 5) * (2 * G::W * 32) + (i & 31);
 #pragma unroll
-    for (int k = 0; k < G::AW; k++) __stcs(base + k * 32, m[k]);
+    for (int k = 0; k < G::W; k++) __stcs(base + k * 32, HL.w[k]);
+#pragma unroll
+    for (int k = 0; k < G::W; k++) __stcs(base + (G::W + k) * 32, VL.w[k]);
 }
 
 template <class SH>
@@ -136,8 +144,13 @@ __global__ void __launch_bounds__(BLOCK) unpack_mask_kernel(const uint32_t *mask
     if (t >= n * G::A) return;
     const long long i = t / G::A;
     const int a = (int)(t - i * G::A);
-    const uint32_t w = mask[(i >> 5) * (G::AW * 32) + (a >> 5) * 32 + (i & 31)];
-    out[t] = (w >> (a & 31)) & 1u;
+    const int r = a / G::ROWA, k = a - r * G::ROWA; // boardConfig.py:45-59
+    const bool vertical = k >= G::C - 1;
+    const int bit = r * G::S + (vertical ? k - (G::C - 1) : k);
+    const uint32_t w = mask[(i >> 5) * (2 * G::W * 32) + ((vertical ? G::W : 0) + (bit >> 5)) * 32 + (i & 31)];
+    const int a_unused = 0;
+    (void)a_unused;
+    out[t] = (w >> (bit & 31)) & 1u;
 }
 
 template <class SH>
@@ -149,9 +162,7 @@ __global__ void __launch_bounds__(BLOCK) legal_kernel(const void *boards, uint32
     load_board<G>(boards, i, b);
     BB<G::W> HL, VL;
     legal_of<SH>(b, HL, VL);
-    uint32_t m[G::AW];
-    swaps_to_actions<G>(HL, VL, m);
-    store_mask<G>(mask, i, m);
+    store_mask<G>(mask, i, HL, VL);
 }
 
 
@@ -172,18 +183,20 @@ __global__ void __launch_bounds__(BLOCK) random_action_kernel(RefillDev rf, cons
     using G = typename SH::G;
     const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
-    uint32_t m[G::AW];
-    load_mask<G>(mask, i, m);
-    const int cnt = mask_count<G>(m);
+    BB<G::W> HL, VL;
+    load_mask<G>(mask, i, HL, VL);
+    const int cnt = swaps_count<G>(HL, VL);
     int a = -1;
     uint32_t st = 0;
     if (cnt == 0) {
         st = ST_NO_LEGAL;
-    } else if (PHILOX) {
-        a = mask_select<G>(m, (int)philox_pick(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr, (uint32_t)cnt));
-    } else {
+    } else if (PHILOX) { // k-th legal swap in swap-bitboard order
+        a = swaps_select<G>(HL, VL, (int)philox_pick(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr, (uint32_t)cnt));
+    } else { // np.random.choice(legal_actions): k-th legal action in ascending action order
         ReplayRng rng;
         rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
+        uint32_t m[G::AW];
+        swaps_to_actions<G>(HL, VL, m);
         a = mask_select<G>(m, (int)rng.below((uint32_t)cnt));
         if (rf.stream_pos) rf.stream_pos[i] = rng.pos;
         if (rng.overflow) st = ST_STREAM_OVERFLOW;
@@ -219,6 +232,12 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards,
 // (static, no atomics); lanes that ask in the same trip receive consecutive boards, so their 16-byte
 // chunk loads/stores stay contiguous inside the 32-board tile.
 constexpr int CHUNK = 256;
+// ECG_BLOCK_LOCKSTEP: keep the warps of a block in the same trip so they share instruction-cache lines
+#if defined(ECG_BLOCK_LOCKSTEP)
+#define ECG_TRIP_ANY(p) __syncthreads_or(p)
+#else
+#define ECG_TRIP_ANY(p) __any_sync(0xffffffffu, p)
+#endif
 
 template <class SH, bool PHILOX>
 __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev &io, long long i,
@@ -227,11 +246,7 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
                                              const BB<SH::G::W> &VL, uint32_t rpos) {
     using G = typename SH::G;
     if (stepped || io.boards_out != io.boards_in) store_board<G>(io.boards_out, i, b);
-    if (io.mask_out) {
-        uint32_t m[G::AW];
-        swaps_to_actions<G>(HL, VL, m);
-        store_mask<G>(io.mask_out, i, m);
-    }
+    if (io.mask_out) store_mask<G>(io.mask_out, i, HL, VL);
     if (io.actions_out) io.actions_out[i] = action;
     if (io.moves_left) io.moves_left[i] = moves;
     if (io.reward) io.reward[i] = reward;
@@ -250,108 +265,126 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
         if (rf.stream_pos) rf.stream_pos[i] = rpos;
 }
 
+#ifndef ECG_STEP_MINB
+#define ECG_STEP_MINB 1
+#endif
 template <class SH, bool PHILOX>
-__global__ void __launch_bounds__(BLOCK) step_kernel(RefillDev rf, StepDev io, long long n) {
+__global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf, StepDev io, int n) {
     using G = typename SH::G;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
-    const long long stride = (((long long)gridDim.x * BLOCK) >> 5) * CHUNK;
+    const int warp = (int)((blockIdx.x * BLOCK + threadIdx.x) >> 5);
+    const int stride = (int)((gridDim.x * BLOCK) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
-    long long chunk0 = warp * CHUNK;
-    long long next = chunk0 < n ? chunk0 : n;
-    long long end = chunk0 + CHUNK < n ? chunk0 + CHUNK : n;
-    if (chunk0 >= n) end = n;
+    int chunk0 = warp * CHUNK;
+    int next = chunk0 < n ? chunk0 : n;
+    int end = chunk0 + CHUNK < n ? chunk0 + CHUNK : n;
 
     Lane<SH> L;
-    long long idx = 0;
-    int moves = 0, action = -1;
+    L.cascades = 0;
+    int idx = 0, moves = 0, action = -1;
     uint32_t rpos = 0; // replay: words consumed since the last reseed
     bool active = false;
     BB<G::W> HL, VL;
 
     for (;;) {
-        // ---- FETCH: idle lanes take the next boards of the cursor
+        // ---- cursor: idle lanes are handed the next boards
         const unsigned need = __ballot_sync(FULL, !active);
+        int cand = n;
         if (need) {
             const int rank = __popc(need & ((1u << lane) - 1u));
             const int cnt = __popc(need);
-            const long long avail = end - next;
-            long long cand;
+            const int avail = end - next;
             if (rank < avail) {
                 cand = next + rank;
-            } else { // the request spills into this warp's next chunk
-                const long long c2 = chunk0 + stride;
-                const long long e2 = c2 + CHUNK < n ? c2 + CHUNK : n;
+            } else if (chunk0 + stride < n) { // the request spills into this warp's next chunk
+                const int c2 = chunk0 + stride;
+                const int e2 = c2 + CHUNK < n ? c2 + CHUNK : n;
                 cand = c2 + (rank - avail);
                 if (cand >= e2) cand = n;
             }
             if (cnt >= avail) {
-                chunk0 += stride;
-                if (chunk0 >= n) {
-                    next = end = n;
-                } else {
+                if (chunk0 + stride < n) {
+                    chunk0 += stride;
                     end = chunk0 + CHUNK < n ? chunk0 + CHUNK : n;
                     next = chunk0 + (cnt - avail);
                     if (next > end) next = end;
+                } else {
+                    chunk0 = next = end = n;
                 }
             } else {
                 next += cnt;
             }
-            if (!active && cand < n) {
-                idx = cand;
-                load_board<G>(io.boards_in, idx, L.bd);
-                moves = io.moves_left ? io.moves_left[idx] : 1;
-                uint32_t st = 0;
-                action = -1;
-                rpos = 0;
-                if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[idx] : 0u;
-                if (moves < 1) { // boardv2.py:44
-                    st = ST_TERMINAL;
-                } else if (io.actions) {
-                    action = io.actions[idx];
-                    if (action < 0 || action >= G::A) {
-                        st = ST_BAD_ACTION;
-                        action = -1;
-                    }
-                } else { // board.random_action(): uniform over the legal set of the current board
-                    uint32_t m[G::AW];
-                    load_mask<G>(io.mask_in, idx, m);
-                    const int c = mask_count<G>(m);
-                    if (c == 0) {
-                        st = ST_NO_LEGAL;
-                    } else {
-                        uint32_t k;
-                        if constexpr (PHILOX) {
-                            k = philox_pick(rf.key, rf.board0 + (unsigned long long)idx, rf.step_ctr, (uint32_t)c);
-                        } else {
-                            ReplayRng rng;
-                            rng.init(rf.stream + idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
-                            k = rng.below((uint32_t)c);
-                            rpos = rng.pos;
-                            if (rng.overflow) st = ST_STREAM_OVERFLOW;
-                        }
-                        action = mask_select<G>(m, (int)k);
-                    }
-                }
-                if (action >= 0) {
-                    rpos = 0; // np.random.seed(cfg.seed) at the top of apply_action (boardv2.py:46)
-                    step_begin<SH>(L, action);
-                    L.status |= st;
-                    moves -= 1;
-                    active = true;
-                } else { // no-op boards are finished on the spot
-                    if (io.mask_out) legal_of<SH>(L.bd, HL, VL);
-                    finish_board<SH, PHILOX>(rf, io, idx, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos);
-                }
+        }
+        const bool fetching = !active && cand < n;
+        if (fetching) idx = cand;
+        // ---- one Philox block per trip for every lane that will refill in this trip: block 0 of the step
+        // substream for a fresh board (word 0 = action pick, words 1..3 = first refill words), block 512*j
+        // for a board entering cascade iteration j
+        uint32_t blk[4];
+        uint32_t blk_index = 0;
+        if constexpr (PHILOX) {
+            if (fetching || active) {
+                blk_index = fetching ? 0u : (uint32_t)L.cascades * 512u;
+                const unsigned long long board = rf.board0 + (unsigned long long)idx;
+                philox4x32_10(blk_index, rf.step_ctr, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)rf.key,
+                              (uint32_t)(rf.key >> 32), blk);
             }
         }
-        if (!__any_sync(FULL, active)) break;
+        // ---- FETCH: load, choose the action, swap, first match pass
+        if (fetching) {
+            load_board<G>(io.boards_in, idx, L.bd);
+            moves = io.moves_left ? io.moves_left[idx] : 1;
+            uint32_t st = 0;
+            action = -1;
+            rpos = 0;
+            if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[idx] : 0u;
+            if (moves < 1) { // boardv2.py:44
+                st = ST_TERMINAL;
+            } else if (io.actions) {
+                action = io.actions[idx];
+                if (action < 0 || action >= G::A) {
+                    st = ST_BAD_ACTION;
+                    action = -1;
+                }
+            } else { // board.random_action(): uniform over the legal set of the current board
+                load_mask<G>(io.mask_in, idx, HL, VL);
+                const int c = swaps_count<G>(HL, VL);
+                if (c == 0) {
+                    st = ST_NO_LEGAL;
+                } else if constexpr (PHILOX) {
+                    action = swaps_select<G>(HL, VL, (int)mulhi32(blk[0], (uint32_t)c));
+                } else { // np.random.choice(legal_actions): ascending action order, numpy's masked rejection
+                    ReplayRng rng;
+                    rng.init(rf.stream + (long long)idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+                    uint32_t m[G::AW];
+                    swaps_to_actions<G>(HL, VL, m);
+                    action = mask_select<G>(m, (int)rng.below((uint32_t)c));
+                    rpos = rng.pos;
+                    if (rng.overflow) st = ST_STREAM_OVERFLOW;
+                }
+            }
+            if (action >= 0) {
+                rpos = 0; // np.random.seed(cfg.seed) at the top of apply_action (boardv2.py:46)
+                step_begin<SH>(L, action);
+                L.status |= st;
+                moves -= 1;
+                active = true;
+            } else { // no-op boards are finished on the spot
+                if (io.mask_out) legal_of<SH>(L.bd, HL, VL);
+                finish_board<SH, PHILOX>(rf, io, idx, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos);
+            }
+        }
+        if (!ECG_TRIP_ANY(active)) break;
         // ---- ITERATE: one cascade iteration on every active lane; FINISH the boards whose cascade ended
         if (active) {
             typename RngOf<PHILOX>::type rng;
-            if constexpr (PHILOX) rng.init(rf.key, rf.board0 + (unsigned long long)idx, rf.step_ctr);
-            else rng.init(rf.stream + idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+            if constexpr (PHILOX) {
+                rng.init(rf.key, rf.board0 + (unsigned long long)idx, rf.step_ctr);
+                rng.preset_block(blk_index, blk);
+            } else {
+                rng.init(rf.stream + (long long)idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+            }
             const bool fin = step_iter<SH>(L, rng, (uint32_t)io.types, HL, VL);
             if constexpr (!PHILOX) rpos = rng.pos;
             if (fin) {
@@ -382,21 +415,20 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(RefillDev rf, void *boar
     uint32_t st = 0, step = rf.step_ctr;
     int done = 0;
     while (moves >= 1) {
-        uint32_t m[G::AW];
-        swaps_to_actions<G>(HL, VL, m);
-        const int cnt = mask_count<G>(m);
+        const int cnt = swaps_count<G>(HL, VL);
         if (cnt == 0) {
             st |= ST_NO_LEGAL;
             break;
         }
-        uint32_t idx;
+        int action;
         if constexpr (PHILOX) {
-            idx = philox_pick(rf.key, board, step, (uint32_t)cnt);
+            action = swaps_select<G>(HL, VL, (int)philox_pick(rf.key, board, step, (uint32_t)cnt));
             rng.init(rf.key, board, step);
         } else {
-            idx = rng.below((uint32_t)cnt);
+            uint32_t m[G::AW];
+            swaps_to_actions<G>(HL, VL, m);
+            action = mask_select<G>(m, (int)rng.below((uint32_t)cnt));
         }
-        const int action = mask_select<G>(m, (int)idx);
         StepOut so;
         step_board<SH>(b, action, (uint32_t)types, rng, so, HL, VL);
         total += so.reward;
@@ -485,11 +517,11 @@ unsigned persistent_grid(K kernel, long long n) {
 
 void op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
     if (wide) {
-        if (philox) step_kernel<SHW, true><<<persistent_grid(step_kernel<SHW, true>, n), BLOCK, 0, s>>>(rf, io, n);
-        else step_kernel<SHW, false><<<persistent_grid(step_kernel<SHW, false>, n), BLOCK, 0, s>>>(rf, io, n);
+        if (philox) step_kernel<SHW, true><<<persistent_grid(step_kernel<SHW, true>, n), BLOCK, 0, s>>>(rf, io, (int)n);
+        else step_kernel<SHW, false><<<persistent_grid(step_kernel<SHW, false>, n), BLOCK, 0, s>>>(rf, io, (int)n);
     } else {
-        if (philox) step_kernel<SHN, true><<<persistent_grid(step_kernel<SHN, true>, n), BLOCK, 0, s>>>(rf, io, n);
-        else step_kernel<SHN, false><<<persistent_grid(step_kernel<SHN, false>, n), BLOCK, 0, s>>>(rf, io, n);
+        if (philox) step_kernel<SHN, true><<<persistent_grid(step_kernel<SHN, true>, n), BLOCK, 0, s>>>(rf, io, (int)n);
+        else step_kernel<SHN, false><<<persistent_grid(step_kernel<SHN, false>, n), BLOCK, 0, s>>>(rf, io, (int)n);
     }
 }
 void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left, long long *total_reward,

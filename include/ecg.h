@@ -53,7 +53,7 @@ typedef struct ecg_config {
     int32_t bits, type_mask, special_type_mask, h_line, v_line, bomb, mega_token; /* boardConfig.py:29-43 */
     int32_t action_space; /* rows * (cols - 1) * 2, boardConfig.py:27 */
     int32_t board_words;  /* u32 words per packed board = 4 planes x ceil(rows*(cols+1)/32) */
-    int32_t mask_words;   /* u32 words per packed legal mask = ceil(action_space/32) */
+    int32_t mask_words;   /* u32 words per packed legal mask = 2 swap bitboards (horizontal, vertical) = board_words/2 */
     int32_t reserved;
 } ecg_config;
 
@@ -122,7 +122,9 @@ int ecg_init_boards(const ecg_config *cfg, const ecg_refill *rf, void *boards, u
 int ecg_legal_mask(const ecg_config *cfg, const void *boards, uint32_t *mask, int64_t n, void *stream);
 
 /* np.random.choice(state.legal_actions) (samplerTasks.py:13): the idx-th legal action, ascending.
- * replay: idx by numpy's masked rejection at stream_pos; philox: idx = mulhi(philox(0xFFFFFFFF, step, board)[0], n) */
+ * replay: idx-th legal action in ascending action order, idx by numpy's masked rejection at stream_pos;
+ * philox: idx = mulhi(word 0 of the (board, step) substream, n), counted in swap-bitboard order (all horizontal
+ * swaps by (row, col), then all vertical swaps) */
 int ecg_random_action(const ecg_config *cfg, const ecg_refill *rf, const uint32_t *mask, int32_t *actions,
                       uint8_t *status, int64_t n, void *stream);
 

@@ -673,7 +673,7 @@ int ecgo_apply_action(const ecgo_cfg *cfg, ecgo_rng *rng, const int64_t *in, int
                 for (int r = 0; r < k; r++) next_state[r * W + col] = 0;
                 for (int r = 0; r < nt; r++) next_state[(k + r) * W + col] = tokens[r];
             }
-            ecgo_rng_seek(rng, (int64_t)(cascades - 1) * 2048);
+            ecgo_rng_seek(rng, (int64_t)(cascades - 1) * 2048 + 1);
             for (int i = 0; i < N; i++)
                 if (next_state[i] == 0) {
                     next_state[i] = 1 + ecgo_rng_digit(rng, (uint32_t)cfg->types);
@@ -930,8 +930,8 @@ int64_t ecgo_random_episode(const ecgo_cfg *cfg, uint32_t seed, int n_moves, int
 }
 
 /* The engine's Philox lockstep episode: at step t the action is the
- * idx-th legal action (ascending), idx = mulhi(philox(ctr=(0xFFFFFFFF, t, board))[0], n_legal);
- * refills come from the (board, t) substream. */
+ * idx-th legal action (ascending), idx = mulhi(word 0 of the (board, t) substream, n_legal);
+ * refills come from the same substream (words j*2048 + 1.. in cascade iteration j). */
 int64_t ecgo_philox_episode(const ecgo_cfg *cfg, uint64_t key, uint64_t board_index, uint32_t step0, int n_moves,
                             int64_t *board_io, int64_t *steps) {
     int64_t next[ECGO_MAX_CELLS], total = 0, nsteps = 0;
@@ -940,9 +940,17 @@ int64_t ecgo_philox_episode(const ecgo_cfg *cfg, uint64_t key, uint64_t board_in
         int legal[ECGO_MAX_ACTIONS];
         int k = ecgo_legal_actions(cfg, board_io, legal);
         if (k == 0) break;
-        uint32_t ctr[4] = {0xFFFFFFFFu, t, (uint32_t)board_index, (uint32_t)(board_index >> 32)}, o[4];
+        uint32_t ctr[4] = {0u, t, (uint32_t)board_index, (uint32_t)(board_index >> 32)}, o[4];
         ecgo_philox4x32_10(ctr, k2, o);
-        int a = legal[(uint32_t)(((uint64_t)o[0] * (uint32_t)k) >> 32)];
+        /* the engine counts the pick in swap-bitboard order: all horizontal swaps by (row, col), then all
+         * vertical swaps by (row, col); within each class ascending action id is already (row, col) order */
+        int ordered[ECGO_MAX_ACTIONS], no = 0;
+        const int per_row = 2 * cfg->cols - 1;
+        for (int j = 0; j < k; j++)
+            if (legal[j] % per_row < cfg->cols - 1) ordered[no++] = legal[j];
+        for (int j = 0; j < k; j++)
+            if (legal[j] % per_row >= cfg->cols - 1) ordered[no++] = legal[j];
+        int a = ordered[(uint32_t)(((uint64_t)o[0] * (uint32_t)k) >> 32)];
         ecgo_rng rng;
         ecgo_rng_init_philox(&rng, key, board_index, t);
         int64_t r;

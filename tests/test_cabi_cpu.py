@@ -46,7 +46,7 @@ def test_config_matches_reference_constants(E):
             assert c.encode(t1, t2) == a == c.encode(t2, t1)
     assert E.BoardConfig(seed=0).seed != 0 and E.BoardConfig().seed  # boardConfig.py:34
     c = E.BoardConfig(seed=1)
-    assert c.native.board_words == 12 and c.native.mask_words == 5  # 48 B boards, 20 B masks
+    assert c.native.board_words == 12 and c.native.mask_words == 6  # 48 B boards, 24 B masks (2 swap bitboards)
     with pytest.raises(Exception):
         object.__setattr__  # frozen
         c.rows = 3
@@ -79,7 +79,7 @@ def test_argument_errors_are_reported_not_raised_in_c(E):
     cfg.board_words = 13  # a config not made by ecg_config_init
     assert L.ecg_legal_mask(C.byref(cfg), None, None, 1, None) < 0
     assert L.ecg_boards_bytes(C.byref(E.BoardConfig(seed=1).native), 33) == 64 * 48
-    assert L.ecg_masks_bytes(C.byref(E.BoardConfig(seed=1).native), 33) == 64 * 20
+    assert L.ecg_masks_bytes(C.byref(E.BoardConfig(seed=1).native), 33) == 64 * 24
 
 
 def test_no_cpu_fallback(E):
