@@ -235,8 +235,10 @@ constexpr int CHUNK = 256;
 // ECG_BLOCK_LOCKSTEP: keep the warps of a block in the same trip so they share instruction-cache lines
 #if defined(ECG_BLOCK_LOCKSTEP)
 #define ECG_TRIP_ANY(p) __syncthreads_or(p)
+#define ECG_PHASE_BARRIER() __syncthreads()
 #else
 #define ECG_TRIP_ANY(p) __any_sync(0xffffffffu, p)
+#define ECG_PHASE_BARRIER() ((void)0)
 #endif
 
 template <class SH, bool PHILOX>
@@ -266,7 +268,7 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
 }
 
 #ifndef ECG_STEP_MINB
-#define ECG_STEP_MINB 1
+#define ECG_STEP_MINB 6
 #endif
 template <class SH, bool PHILOX>
 __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf, StepDev io, int n) {
@@ -331,6 +333,7 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf
                               (uint32_t)(rf.key >> 32), blk);
             }
         }
+        ECG_PHASE_BARRIER();
         // ---- FETCH: load, choose the action, swap, first match pass
         if (fetching) {
             load_board<G>(io.boards_in, idx, L.bd);
@@ -393,6 +396,7 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf
                 active = false;
             }
         }
+        ECG_PHASE_BARRIER();
     }
 }
 

@@ -13,6 +13,14 @@ SHAPES = [(9, 9, 6), (6, 6, 4), (12, 12, 7), (16, 16, 8), (6, 6, 3), (5, 5, 2)]
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # build what a fresh checkout lacks (built artefacts are git-ignored): the CUDA library (nvcc cross-compiles
+    # without a GPU) and the CPU oracle; the host simulator builds itself on first use
+    lib = os.path.join(ROOT, "element-crush-gym_b200", "lib", "libecg.so")
+    if not os.path.exists(lib):
+        import importlib
+        importlib.import_module("element-crush-gym_b200.build").build()
+    from oracle import oracle as _o
+    _o.build()
 
 
 @pytest.fixture(scope="session")
