@@ -274,6 +274,7 @@ int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const
     if (check_cfg(cfg) || check_refill(rf)) return -1;
     if (!boards || !moves_left || !total_reward) return fail("ecg_rollout: boards, moves_left and total_reward are required");
     if (n <= 0) return 0;
+    if (n > (1ll << 30)) return fail("ecg_rollout: at most 2^30 boards per call");
     ops_for(cfg->rows)->rollout(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), boards, moves_left,
                                 (long long *)total_reward, steps_done, status, cfg->types, n, (cudaStream_t)stream);
     return check_launch("ecg_rollout");

@@ -270,10 +270,26 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
 #ifndef ECG_STEP_MINB
 #define ECG_STEP_MINB 6
 #endif
-template <class SH, bool PHILOX>
-__global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf, StepDev io, int n) {
+
+struct RolloutDev {
+    void *boards;
+    const int32_t *moves_left;
+    long long *total_reward;
+    int32_t *steps_done;
+    uint8_t *status;
+};
+
+// One kernel for the lockstep step (ROLLOUT = false: every board takes ONE action, all per-step outputs are
+// written) and for whole-episode rollouts (ROLLOUT = true: a board keeps stepping with random legal actions
+// until moves_left reaches 0; only the final board and the collected reward go back to HBM).
+// Lane states: IDLE (needs a board) -> READY (board + legal swaps in registers, action not chosen yet)
+//              -> ACTIVE (inside the cascade loop) -> IDLE | READY (rollout: next action of the same board).
+template <class SH, bool PHILOX, bool ROLLOUT>
+__global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf, StepDev io, RolloutDev ro, int types,
+                                                                    int n) {
     using G = typename SH::G;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int IDLE = 0, READY = 1, ACTIVE = 2;
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * BLOCK + threadIdx.x) >> 5);
     const int stride = (int)((gridDim.x * BLOCK) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
@@ -284,14 +300,18 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf
 
     Lane<SH> L;
     L.cascades = 0;
+    int state = IDLE;
     int idx = 0, moves = 0, action = -1;
-    uint32_t rpos = 0; // replay: words consumed since the last reseed
-    bool active = false;
+    uint32_t step = rf.step_ctr; // philox step counter of this lane's board (advances inside a rollout)
+    uint32_t rpos = 0;           // replay: words consumed since the last reseed
+    long long total = 0;         // rollout: points collected so far
+    int steps_done = 0;
+    uint32_t st_acc = 0;
     BB<G::W> HL, VL;
 
     for (;;) {
         // ---- cursor: idle lanes are handed the next boards
-        const unsigned need = __ballot_sync(FULL, !active);
+        const unsigned need = __ballot_sync(FULL, state == IDLE);
         int cand = n;
         if (need) {
             const int rank = __popc(need & ((1u << lane) - 1u));
@@ -318,40 +338,52 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf
                 next += cnt;
             }
         }
-        const bool fetching = !active && cand < n;
-        if (fetching) idx = cand;
-        // ---- one Philox block per trip for every lane that will refill in this trip: block 0 of the step
-        // substream for a fresh board (word 0 = action pick, words 1..3 = first refill words), block 512*j
-        // for a board entering cascade iteration j
+        // ---- LOAD: IDLE -> READY
+        if (state == IDLE && cand < n) {
+            idx = cand;
+            step = rf.step_ctr;
+            rpos = 0;
+            if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[idx] : 0u;
+            if constexpr (ROLLOUT) {
+                load_board<G>(ro.boards, idx, L.bd);
+                moves = ro.moves_left[idx];
+                total = 0;
+                steps_done = 0;
+                st_acc = 0;
+                legal_of<SH>(L.bd, HL, VL);
+            } else {
+                load_board<G>(io.boards_in, idx, L.bd);
+                moves = io.moves_left ? io.moves_left[idx] : 1;
+                if (!io.actions) load_mask<G>(io.mask_in, idx, HL, VL);
+            }
+            state = READY;
+        }
+        // ---- one Philox block per trip for every lane that needs random words in this trip: block 0 of the
+        // (board, step) substream for a READY lane (word 0 = action pick, words 1..3 = first refill words),
+        // block 512*j for a lane entering cascade iteration j
         uint32_t blk[4];
         uint32_t blk_index = 0;
         if constexpr (PHILOX) {
-            if (fetching || active) {
-                blk_index = fetching ? 0u : (uint32_t)L.cascades * 512u;
+            if (state != IDLE) {
+                blk_index = state == READY ? 0u : (uint32_t)L.cascades * 512u;
                 const unsigned long long board = rf.board0 + (unsigned long long)idx;
-                philox4x32_10(blk_index, rf.step_ctr, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)rf.key,
+                philox4x32_10(blk_index, step, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)rf.key,
                               (uint32_t)(rf.key >> 32), blk);
             }
         }
-        ECG_PHASE_BARRIER();
-        // ---- FETCH: load, choose the action, swap, first match pass
-        if (fetching) {
-            load_board<G>(io.boards_in, idx, L.bd);
-            moves = io.moves_left ? io.moves_left[idx] : 1;
+        // ---- BEGIN: READY -> ACTIVE: choose the action, swap, first match pass
+        if (state == READY) {
             uint32_t st = 0;
             action = -1;
-            rpos = 0;
-            if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[idx] : 0u;
             if (moves < 1) { // boardv2.py:44
                 st = ST_TERMINAL;
-            } else if (io.actions) {
+            } else if (!ROLLOUT && io.actions) {
                 action = io.actions[idx];
                 if (action < 0 || action >= G::A) {
                     st = ST_BAD_ACTION;
                     action = -1;
                 }
             } else { // board.random_action(): uniform over the legal set of the current board
-                load_mask<G>(io.mask_in, idx, HL, VL);
                 const int c = swaps_count<G>(HL, VL);
                 if (c == 0) {
                     st = ST_NO_LEGAL;
@@ -372,82 +404,51 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) step_kernel(RefillDev rf
                 step_begin<SH>(L, action);
                 L.status |= st;
                 moves -= 1;
-                active = true;
+                state = ACTIVE;
+            } else if constexpr (ROLLOUT) { // the episode is over (terminal, or nothing legal)
+                if (st != ST_TERMINAL) st_acc |= st;
+                store_board<G>(ro.boards, idx, L.bd);
+                ro.total_reward[idx] = total;
+                if (ro.steps_done) ro.steps_done[idx] = steps_done;
+                if (ro.status) ro.status[idx] = (uint8_t)st_acc;
+                if constexpr (!PHILOX)
+                    if (rf.stream_pos) rf.stream_pos[idx] = rpos;
+                state = IDLE;
             } else { // no-op boards are finished on the spot
                 if (io.mask_out) legal_of<SH>(L.bd, HL, VL);
                 finish_board<SH, PHILOX>(rf, io, idx, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos);
+                state = IDLE;
             }
         }
-        if (!ECG_TRIP_ANY(active)) break;
-        // ---- ITERATE: one cascade iteration on every active lane; FINISH the boards whose cascade ended
-        if (active) {
+        if (!ECG_TRIP_ANY(state != IDLE)) break;
+        // ---- ITERATE: one cascade iteration on every active lane; FINISH the steps whose cascade ended
+        if (state == ACTIVE) {
             typename RngOf<PHILOX>::type rng;
             if constexpr (PHILOX) {
-                rng.init(rf.key, rf.board0 + (unsigned long long)idx, rf.step_ctr);
+                rng.init(rf.key, rf.board0 + (unsigned long long)idx, step);
                 rng.preset_block(blk_index, blk);
             } else {
                 rng.init(rf.stream + (long long)idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
             }
-            const bool fin = step_iter<SH>(L, rng, (uint32_t)io.types, HL, VL);
+            const bool fin = step_iter<SH>(L, rng, (uint32_t)types, HL, VL);
             if constexpr (!PHILOX) rpos = rng.pos;
             if (fin) {
-                finish_board<SH, PHILOX>(rf, io, idx, L.bd, true, action, moves, L.reward, L.cascades, L.status, HL, VL,
-                                         rpos);
-                active = false;
+                if constexpr (ROLLOUT) {
+                    total += L.reward;
+                    st_acc |= L.status;
+                    steps_done++;
+                    step++;
+                    if (st_acc & ST_STREAM_OVERFLOW) moves = 0; // invalid from here on: end the episode
+                    state = READY; // next action of this board (or the end of the episode)
+                } else {
+                    finish_board<SH, PHILOX>(rf, io, idx, L.bd, true, action, moves, L.reward, L.cascades, L.status, HL,
+                                             VL, rpos);
+                    state = IDLE;
+                }
             }
         }
         ECG_PHASE_BARRIER();
     }
-}
-
-template <class SH, bool PHILOX>
-__global__ void __launch_bounds__(BLOCK) rollout_kernel(RefillDev rf, void *boards, const int32_t *moves_left,
-                                                        long long *total_reward, int32_t *steps_done, uint8_t *status,
-                                                        int types, long long n) {
-    using G = typename SH::G;
-    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= n) return;
-    Board<G> b;
-    load_board<G>(boards, i, b);
-    int moves = moves_left[i];
-    typename RngOf<PHILOX>::type rng;
-    const unsigned long long board = rf.board0 + (unsigned long long)i;
-    if constexpr (!PHILOX) rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
-    BB<G::W> HL, VL;
-    legal_of<SH>(b, HL, VL);
-    long long total = 0;
-    uint32_t st = 0, step = rf.step_ctr;
-    int done = 0;
-    while (moves >= 1) {
-        const int cnt = swaps_count<G>(HL, VL);
-        if (cnt == 0) {
-            st |= ST_NO_LEGAL;
-            break;
-        }
-        int action;
-        if constexpr (PHILOX) {
-            action = swaps_select<G>(HL, VL, (int)philox_pick(rf.key, board, step, (uint32_t)cnt));
-            rng.init(rf.key, board, step);
-        } else {
-            uint32_t m[G::AW];
-            swaps_to_actions<G>(HL, VL, m);
-            action = mask_select<G>(m, (int)rng.below((uint32_t)cnt));
-        }
-        StepOut so;
-        step_board<SH>(b, action, (uint32_t)types, rng, so, HL, VL);
-        total += so.reward;
-        st |= so.status;
-        moves--;
-        step++;
-        done++;
-        if (st & ST_STREAM_OVERFLOW) break;
-    }
-    store_board<G>(boards, i, b);
-    total_reward[i] = total;
-    if (steps_done) steps_done[i] = done;
-    if (status) status[i] = (uint8_t)st;
-    if constexpr (!PHILOX)
-        if (rf.stream_pos) rf.stream_pos[i] = rng.pos;
 }
 
 // ------------------------------------------------------------------ launchers
@@ -519,24 +520,32 @@ unsigned persistent_grid(K kernel, long long n) {
     return (unsigned)(blocks < resident ? blocks : resident);
 }
 
+template <class SH, bool PHILOX, bool ROLLOUT>
+void launch_lanes(RefillDev rf, StepDev io, RolloutDev ro, int types, long long n, cudaStream_t s) {
+    lane_kernel<SH, PHILOX, ROLLOUT>
+        <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT>, n), BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
+}
+
 void op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
+    const RolloutDev ro = {};
     if (wide) {
-        if (philox) step_kernel<SHW, true><<<persistent_grid(step_kernel<SHW, true>, n), BLOCK, 0, s>>>(rf, io, (int)n);
-        else step_kernel<SHW, false><<<persistent_grid(step_kernel<SHW, false>, n), BLOCK, 0, s>>>(rf, io, (int)n);
+        if (philox) launch_lanes<SHW, true, false>(rf, io, ro, io.types, n, s);
+        else launch_lanes<SHW, false, false>(rf, io, ro, io.types, n, s);
     } else {
-        if (philox) step_kernel<SHN, true><<<persistent_grid(step_kernel<SHN, true>, n), BLOCK, 0, s>>>(rf, io, (int)n);
-        else step_kernel<SHN, false><<<persistent_grid(step_kernel<SHN, false>, n), BLOCK, 0, s>>>(rf, io, (int)n);
+        if (philox) launch_lanes<SHN, true, false>(rf, io, ro, io.types, n, s);
+        else launch_lanes<SHN, false, false>(rf, io, ro, io.types, n, s);
     }
 }
 void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left, long long *total_reward,
                 int32_t *steps_done, uint8_t *status, int types, long long n, cudaStream_t s) {
-    const unsigned g = grid_for(n, BLOCK);
+    const StepDev io = {};
+    const RolloutDev ro = {boards, moves_left, total_reward, steps_done, status};
     if (wide) {
-        if (philox) rollout_kernel<SHW, true><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
-        else rollout_kernel<SHW, false><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
+        if (philox) launch_lanes<SHW, true, true>(rf, io, ro, types, n, s);
+        else launch_lanes<SHW, false, true>(rf, io, ro, types, n, s);
     } else {
-        if (philox) rollout_kernel<SHN, true><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
-        else rollout_kernel<SHN, false><<<g, BLOCK, 0, s>>>(rf, boards, moves_left, total_reward, steps_done, status, types, n);
+        if (philox) launch_lanes<SHN, true, true>(rf, io, ro, types, n, s);
+        else launch_lanes<SHN, false, true>(rf, io, ro, types, n, s);
     }
 }
 
