@@ -18,6 +18,7 @@ from .boards import BatchedBoards, fresh_key
 from .env import BatchedMatch3Env, HostStepper, Match3Env
 from .state import BoardV2
 from . import dist
+from .mcts import BatchedRolloutMCTS
 
 __all__ = ["BoardConfig", "BoardV2", "BatchedBoards", "BatchedMatch3Env", "Match3Env", "HostStepper", "dist",
-           "EcgError", "fresh_key"]
+           "EcgError", "fresh_key", "BatchedRolloutMCTS"]
