@@ -40,7 +40,7 @@ class StepIO(C.Structure):
                 ("mask_in", C.c_void_p), ("actions_out", C.c_void_p), ("moves_left", C.c_void_p),
                 ("reward", C.c_void_p), ("score", C.c_void_p), ("cascades", C.c_void_p),
                 ("mask_out", C.c_void_p), ("flags", C.c_void_p), ("status", C.c_void_p),
-                ("env_goal", C.c_int32), ("reserved", C.c_int32)]
+                ("env_goal", C.c_int32), ("reserved", C.c_int32), ("src_index", C.c_void_p)]
 
 
 EXPORTS = {
@@ -63,6 +63,7 @@ EXPORTS = {
     "ecg_rollout": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_episode_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ecg_observe_onehot": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
 }
 
 _lib = None

@@ -246,23 +246,78 @@ class BatchedBoards:
         c.stream_pos = None if self.stream_pos is None else self.stream_pos.clone()
         return c
 
+    def expand(self):
+        """Every legal (board, action) pair stepped once, in ONE kernel (Node.expand for all children,
+        mctslib/standard/mcts.py:31-42; the inner loop of greedy_action, boardv2.py:209-218).
+        Returns (children: BatchedBoards with one board per pair, parent: int64 [P], action: int32 [P]);
+        pairs are ordered by (board, ascending action).  A child uses its parent's refill stream / Philox id,
+        like the reference where every child is stepped with np.random.seed(cfg.seed)."""
+        legal = self.legal_mask() & (self.moves_left >= 1)[:, None]  # terminal boards have no children (boardv2.py:44)
+        pairs = torch.nonzero(legal, as_tuple=False)  # sorted by (board, action)
+        parent = pairs[:, 0].contiguous()
+        action = pairs[:, 1].to(torch.int32).contiguous()
+        p = int(parent.numel())
+        child = BatchedBoards(self.cfg, p, device=self.device, refill=self.refill_mode, key=self.key,
+                              board0=self.board0, env_goal=self.env_goal, _empty=True)
+        child.stream, child.stream_len, child.stream_stride = self.stream, self.stream_len, self.stream_stride
+        child.step_ctr = self.step_ctr + 1
+        if p == 0:
+            return child, parent, action
+        src = parent.to(torch.int32).contiguous()
+        io = N.StepIO()
+        io.boards_in = self.boards.data_ptr()
+        io.boards_out = child.boards.data_ptr()
+        io.actions = action.data_ptr()
+        io.src_index = src.data_ptr()
+        io.actions_out = child.last_actions.data_ptr()
+        io.reward = child.step_reward.data_ptr()
+        io.cascades = child.cascades.data_ptr()
+        io.mask_out = child.mask.data_ptr()
+        io.status = child.status.data_ptr()
+        io.env_goal = self.env_goal
+        rf = self._refill()
+        if self.refill_mode == "replay":
+            rf.stream_pos = None  # every child restarts the stream (np.random.seed at the top of apply_action)
+        N.check(self.L.ecg_step(C.byref(self.nat), C.byref(rf), C.byref(io), p, _stream(self.device)), "ecg_step")
+        child.moves_left.copy_(self.moves_left[parent] - 1)
+        child.score.copy_(self.score[parent] + child.step_reward)
+        child._mask_valid = True
+        if self.refill_mode == "replay":  # a child continues on its parent's stream (strided per parent board)
+            child.stream_pos = torch.zeros(p, dtype=torch.int32, device=self.device)
+            child._stream_src = src
+        return child, parent, action
+
     def greedy_action(self) -> torch.Tensor:
-        """argmax over legal actions of the one-step reward, first maximum wins (boardv2.py:209-218).
-        Expands all children: one step kernel per action id over cloned boards."""
-        legal = self.legal_mask()
+        """argmax over legal actions of the one-step reward, first maximum wins (boardv2.py:209-218); -1 for a
+        board without legal action.  One expansion kernel + a segmented arg-max."""
+        child, parent, action = self.expand()
         best = torch.full((self.n,), -1, dtype=torch.int32, device=self.device)
-        best_r = torch.full((self.n,), -1, dtype=torch.int64, device=self.device)
-        for a in range(self.cfg.action_space):
-            col = legal[:, a]
-            if not bool(col.any()):
-                continue
-            child = self.clone()
-            child.apply_action(torch.full((self.n,), a, dtype=torch.int32, device=self.device))
-            r = torch.where(col, child.reward, torch.full_like(best_r, -1))
-            better = r > best_r
-            best = torch.where(better, torch.full_like(best, a), best)
-            best_r = torch.where(better, r, best_r)
+        if parent.numel() == 0:
+            return best
+        r = child.step_reward.to(torch.int64)
+        top = torch.full((self.n,), -1, dtype=torch.int64, device=self.device)
+        top.scatter_reduce_(0, parent, r, reduce="amax", include_self=True)
+        is_top = r == top[parent]
+        # first maximum = smallest action among the maxima
+        big = torch.full((self.n,), 1 << 30, dtype=torch.int64, device=self.device)
+        cand = torch.where(is_top, action.to(torch.int64), torch.full_like(r, 1 << 30))
+        big.scatter_reduce_(0, parent, cand, reduce="amin", include_self=True)
+        has = big < (1 << 30)
+        best[has] = big[has].to(torch.int32)
         return best
+
+    def observe_onehot(self, channels: int = None, dtype=torch.float32, out=None) -> torch.Tensor:
+        """[N, rows, cols, channels] one-hot of the cell values = nnx.one_hot(board.array, channels) with
+        channels = 2 ** (ceil(log2(types)) + 2) (elementCrush.py:66,92); values >= channels give all zeros."""
+        import math
+        if channels is None:
+            channels = 2 ** (int(math.ceil(math.log2(self.cfg.types))) + 2)
+        kind = {torch.uint8: 0, torch.float32: 1, torch.bfloat16: 2, torch.float16: 3}[dtype]
+        if out is None:
+            out = torch.empty((self.n, self.cfg.rows, self.cfg.columns, channels), dtype=dtype, device=self.device)
+        N.check(self.L.ecg_observe_onehot(C.byref(self.nat), _ptr(self.boards), _ptr(out), channels, kind, self.n,
+                                          _stream(self.device)), "ecg_observe_onehot")
+        return out
 
     # ------------------------------------------------------------------ statistics
     def episode_stats(self) -> torch.Tensor:

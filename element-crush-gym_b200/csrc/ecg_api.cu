@@ -250,6 +250,7 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
     if (io->flags && !(io->score && io->moves_left)) return fail("ecg_step: flags need score and moves_left");
     if (n <= 0) return 0;
     if (n > (1ll << 30)) return fail("ecg_step: at most 2^30 boards per call");
+    if (io->src_index && io->boards_out == io->boards_in) return fail("ecg_step: src_index needs boards_out != boards_in");
     StepDev sd;
     sd.boards_in = io->boards_in;
     sd.boards_out = io->boards_out;
@@ -265,6 +266,7 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
     sd.status = io->status;
     sd.env_goal = io->env_goal;
     sd.types = cfg->types;
+    sd.src_index = io->src_index;
     ops_for(cfg->rows)->step(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), sd, n, (cudaStream_t)stream);
     return check_launch("ecg_step");
 }
@@ -278,6 +280,17 @@ int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const
     ops_for(cfg->rows)->rollout(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), boards, moves_left,
                                 (long long *)total_reward, steps_done, status, cfg->types, n, (cudaStream_t)stream);
     return check_launch("ecg_rollout");
+}
+
+int ecg_observe_onehot(const ecg_config *cfg, const void *boards, void *out, int channels, int elem_kind, int64_t n,
+                       void *stream) {
+    if (check_cfg(cfg)) return -1;
+    if (!boards || !out) return fail("ecg_observe_onehot: NULL buffer");
+    if (channels < 1 || channels > 256) return fail("ecg_observe_onehot: channels must be in 1..256");
+    if (elem_kind < 0 || elem_kind > 3) return fail("ecg_observe_onehot: elem_kind 0=u8 1=f32 2=bf16 3=f16");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->onehot(boards, out, channels, elem_kind, cfg->types, n, (cudaStream_t)stream);
+    return check_launch("ecg_observe_onehot");
 }
 
 int ecg_episode_stats(const int32_t *score, const uint8_t *flags, int64_t *out, int64_t n, void *stream) {

@@ -24,6 +24,7 @@ struct StepDev {
     uint32_t *mask_out;
     uint8_t *flags, *status;
     int env_goal, types;
+    const int32_t *src_index;
 };
 
 // `wide` selects the types >= 8 instantiation (4 token planes + np.clip(.., 0, 32) quirk)
@@ -41,6 +42,7 @@ struct ShapeOps {
     void (*rollout)(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left,
                     long long *total_reward, int32_t *steps_done, uint8_t *status, int types, long long n,
                     cudaStream_t s);
+    void (*onehot)(const void *boards, void *out, int channels, int elem_kind, int types, long long n, cudaStream_t s);
 };
 
 const ShapeOps *shape_ops_5();

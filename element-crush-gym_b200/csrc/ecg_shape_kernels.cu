@@ -153,6 +153,30 @@ __global__ void __launch_bounds__(BLOCK) unpack_mask_kernel(const uint32_t *mask
     out[t] = (w >> (bit & 31)) & 1u;
 }
 
+// nnx.one_hot(board.array, channels) (elementCrush.py:92): one thread per (board, cell) writes `channels` values
+template <class SH, typename T>
+__global__ void __launch_bounds__(BLOCK) onehot_kernel(const void *boards, T *__restrict__ out, int channels, T one,
+                                                       int types, long long n) {
+    using G = typename SH::G;
+    const long long t = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (t >= n * (G::R * G::C)) return;
+    const long long i = t / (G::R * G::C);
+    const int cell = (int)(t - i * (G::R * G::C));
+    const int r = cell / G::C, c = cell - r * G::C, bit = r * G::S + c;
+    constexpr int CH = G::W; // chunks of 4 words: word index plane*W + (bit >> 5)
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(boards) + (i >> 5) * (CH * 32 * 4);
+    int code = 0;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int j = p * G::W + (bit >> 5);
+        const uint32_t x = w[((j >> 2) * 32 + (int)(i & 31)) * 4 + (j & 3)];
+        code |= (int)((x >> (bit & 31)) & 1u) << p;
+    }
+    const int value = decode_cell(make_codec(types), code);
+    T *dst = out + t * channels;
+    for (int k = 0; k < channels; k++) dst[k] = k == value ? one : (T)0;
+}
+
 template <class SH>
 __global__ void __launch_bounds__(BLOCK) legal_kernel(const void *boards, uint32_t *mask, long long n) {
     using G = typename SH::G;
@@ -242,7 +266,7 @@ constexpr int CHUNK = 256;
 #endif
 
 template <class SH, bool PHILOX>
-__device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev &io, long long i,
+__device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev &io, long long i, long long src,
                                              const Board<typename SH::G> &b, bool stepped, int action, int moves,
                                              int reward, int cascades, uint32_t status, const BB<SH::G::W> &HL,
                                              const BB<SH::G::W> &VL, uint32_t rpos) {
@@ -254,7 +278,7 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
     if (io.reward) io.reward[i] = reward;
     int score = reward;
     if (io.score) {
-        score += io.score[i];
+        score += io.score[src];
         io.score[i] = score;
     }
     if (io.cascades) io.cascades[i] = cascades;
@@ -302,6 +326,7 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
     L.cascades = 0;
     int state = IDLE;
     int idx = 0, moves = 0, action = -1;
+    int src = 0; // board whose state, refill stream and Philox id this job uses (== idx unless io.src_index)
     uint32_t step = rf.step_ctr; // philox step counter of this lane's board (advances inside a rollout)
     uint32_t rpos = 0;           // replay: words consumed since the last reseed
     long long total = 0;         // rollout: points collected so far
@@ -341,9 +366,12 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
         // ---- LOAD: IDLE -> READY
         if (state == IDLE && cand < n) {
             idx = cand;
+            src = idx;
+            if constexpr (!ROLLOUT)
+                if (io.src_index) src = io.src_index[idx];
             step = rf.step_ctr;
             rpos = 0;
-            if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[idx] : 0u;
+            if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[src] : 0u;
             if constexpr (ROLLOUT) {
                 load_board<G>(ro.boards, idx, L.bd);
                 moves = ro.moves_left[idx];
@@ -352,9 +380,9 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
                 st_acc = 0;
                 legal_of<SH>(L.bd, HL, VL);
             } else {
-                load_board<G>(io.boards_in, idx, L.bd);
-                moves = io.moves_left ? io.moves_left[idx] : 1;
-                if (!io.actions) load_mask<G>(io.mask_in, idx, HL, VL);
+                load_board<G>(io.boards_in, src, L.bd);
+                moves = io.moves_left ? io.moves_left[src] : 1;
+                if (!io.actions) load_mask<G>(io.mask_in, src, HL, VL);
             }
             state = READY;
         }
@@ -366,7 +394,7 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
         if constexpr (PHILOX) {
             if (state != IDLE) {
                 blk_index = state == READY ? 0u : (uint32_t)L.cascades * 512u;
-                const unsigned long long board = rf.board0 + (unsigned long long)idx;
+                const unsigned long long board = rf.board0 + (unsigned long long)src;
                 philox4x32_10(blk_index, step, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)rf.key,
                               (uint32_t)(rf.key >> 32), blk);
             }
@@ -391,7 +419,7 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
                     action = swaps_select<G>(HL, VL, (int)mulhi32(blk[0], (uint32_t)c));
                 } else { // np.random.choice(legal_actions): ascending action order, numpy's masked rejection
                     ReplayRng rng;
-                    rng.init(rf.stream + (long long)idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+                    rng.init(rf.stream + (long long)src * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
                     uint32_t m[G::AW];
                     swaps_to_actions<G>(HL, VL, m);
                     action = mask_select<G>(m, (int)rng.below((uint32_t)c));
@@ -416,7 +444,7 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
                 state = IDLE;
             } else { // no-op boards are finished on the spot
                 if (io.mask_out) legal_of<SH>(L.bd, HL, VL);
-                finish_board<SH, PHILOX>(rf, io, idx, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos);
+                finish_board<SH, PHILOX>(rf, io, idx, src, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos);
                 state = IDLE;
             }
         }
@@ -425,10 +453,10 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
         if (state == ACTIVE) {
             typename RngOf<PHILOX>::type rng;
             if constexpr (PHILOX) {
-                rng.init(rf.key, rf.board0 + (unsigned long long)idx, step);
+                rng.init(rf.key, rf.board0 + (unsigned long long)src, step);
                 rng.preset_block(blk_index, blk);
             } else {
-                rng.init(rf.stream + (long long)idx * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+                rng.init(rf.stream + (long long)src * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
             }
             const bool fin = step_iter<SH>(L, rng, (uint32_t)types, HL, VL);
             if constexpr (!PHILOX) rpos = rng.pos;
@@ -441,8 +469,8 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
                     if (st_acc & ST_STREAM_OVERFLOW) moves = 0; // invalid from here on: end the episode
                     state = READY; // next action of this board (or the end of the episode)
                 } else {
-                    finish_board<SH, PHILOX>(rf, io, idx, L.bd, true, action, moves, L.reward, L.cascades, L.status, HL,
-                                             VL, rpos);
+                    finish_board<SH, PHILOX>(rf, io, idx, src, L.bd, true, action, moves, L.reward, L.cascades, L.status,
+                                             HL, VL, rpos);
                     state = IDLE;
                 }
             }
@@ -549,7 +577,16 @@ void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_
     }
 }
 
-const ShapeOps k_ops = {op_pack, op_unpack, op_unpack_mask, op_init, op_legal, op_random_action, op_step, op_rollout};
+void op_onehot(const void *boards, void *out, int channels, int elem_kind, int types, long long n, cudaStream_t s) {
+    const unsigned g = grid_for(n * SHN::G::R * SHN::G::C, BLOCK);
+    if (elem_kind == 0) onehot_kernel<SHN, uint8_t><<<g, BLOCK, 0, s>>>(boards, (uint8_t *)out, channels, (uint8_t)1, types, n);
+    else if (elem_kind == 1) onehot_kernel<SHN, uint32_t><<<g, BLOCK, 0, s>>>(boards, (uint32_t *)out, channels, 0x3F800000u, types, n);
+    else onehot_kernel<SHN, uint16_t><<<g, BLOCK, 0, s>>>(boards, (uint16_t *)out, channels,
+                                                          (uint16_t)(elem_kind == 2 ? 0x3F80 : 0x3C00), types, n);
+}
+
+const ShapeOps k_ops = {op_pack, op_unpack, op_unpack_mask, op_init, op_legal, op_random_action, op_step, op_rollout,
+                        op_onehot};
 
 } // namespace
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ECG_VERSION 100
+#define ECG_VERSION 101
 
 /* per-board status bits */
 #define ECG_ST_TERMINAL 1        /* n_actions < 1: board returned unchanged (boardv2.py:44-45) */
@@ -87,6 +87,10 @@ typedef struct ecg_step_io {
     uint8_t *status;         /* optional out [n]: ECG_ST_* */
     int32_t env_goal;        /* env.py:17 env_goal */
     int32_t reserved;
+    const int32_t *src_index; /* optional [n]: job i steps board src_index[i] of boards_in (and uses that board's
+                                 refill stream / Philox id, moves_left, score, mask_in) and writes every output at i:
+                                 "expand these (board, action) pairs" = Node.expand / greedy_action (boardv2.py:209-218,
+                                 mctslib/standard/mcts.py:31-42).  Needs boards_out != boards_in. */
 } ecg_step_io;
 
 int ecg_version(void);
@@ -136,6 +140,12 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
  * collected; steps_done (optional, [n]) the number of actions applied. */
 int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
                 int64_t *total_reward, int32_t *steps_done, uint8_t *status, int64_t n, void *stream);
+
+/* Observation for the policy/value net: nnx.one_hot(board.array, channels) (elementCrush.py:66,92), layout
+ * [n, rows, cols, channels]; a cell value >= channels (e.g. the mega token, 32 of 32 channels) is all zeros, as in
+ * jax.nn.one_hot.  elem_kind: 0 = uint8, 1 = float32, 2 = bfloat16, 3 = float16. */
+int ecg_observe_onehot(const ecg_config *cfg, const void *boards, void *out, int channels, int elem_kind, int64_t n,
+                       void *stream);
 
 /* episode statistics (main.py:240-267 sample()): out[0]=sum(score) out[1]=n out[2]=min out[3]=max
  * out[4]=#flags&WON out[5]=sum(score^2); out must be zero-initialised except out[2]=INT64_MAX, out[3]=INT64_MIN */

@@ -361,3 +361,57 @@ def test_full_size_properties(E):
     m1 = bb.packed_mask().clone()
     bb._mask_valid = False
     assert torch.equal(m1, bb.packed_mask())
+
+
+def test_expand_and_greedy_vs_oracle(E):
+    """All legal children of every board in one kernel (Node.expand / greedy_action, boardv2.py:209-218)."""
+    shape = (9, 9, 6)
+    o = Oracle(*shape)
+    n = 257
+    seeds = np.arange(100, 100 + n, dtype=np.int64)
+    bb = E.BatchedBoards(cfg_of(E, shape), n, 5, refill="replay", seeds=seeds, stream_len=2048)
+    boards = np_(bb.array)
+    child, parent, action = bb.expand()
+    parent, action = np_(parent), np_(action)
+    legal = o.legal_mask_batch(boards)
+    pi, ai = np.nonzero(legal)
+    assert np.array_equal(parent, pi) and np.array_equal(action, ai)
+    raw = np.stack([Oracle.mt_raw(int(s), 2048) for s in seeds])
+    res = o.step_batch(boards[parent], action, mode="replay", raw=raw[parent])
+    assert np.array_equal(np_(child.array), res["boards"])
+    assert np.array_equal(np_(child.step_reward), res["reward"])
+    assert np.array_equal(np_(child.legal_mask()), res["legal"])
+    assert (np_(child.moves_left) == 4).all() and np.array_equal(np_(child.reward), res["reward"])
+    # greedy: first maximum over ascending legal actions
+    want = np.full(n, -1)
+    for b in range(n):
+        sel = parent == b
+        if sel.any():
+            r = res["reward"][sel]
+            want[b] = action[sel][np.argmax(r)]
+    assert np.array_equal(np_(bb.greedy_action()), want)
+    # philox mode: children share the parent's (board, step) substream
+    pb = E.BatchedBoards(cfg_of(E, shape), n, 5, arrays=boards, key=KEY, board0=50)
+    pb.step_ctr = 3
+    ch, par, act = pb.expand()
+    par, act = np_(par), np_(act)
+    for j in range(0, len(par), 37):
+        r1 = o.step_batch(boards[par[j]:par[j] + 1], act[j:j + 1], mode="philox", key=KEY, board0=50 + int(par[j]), step_ctr=3)
+        assert np.array_equal(np_(ch.array[j:j + 1]), r1["boards"]) and int(ch.step_reward[j]) == r1["reward"][0]
+
+
+def test_onehot_observation(E):
+    import torch
+    for shape in ((9, 9, 6), (16, 16, 8), (6, 6, 4)):
+        o = Oracle(*shape)
+        rng = np.random.default_rng(3)
+        vals = np.array(list(range(0, shape[2] + 1)) + [o.cfg.h_line, o.cfg.v_line, o.cfg.bomb, o.cfg.mega_token])
+        b = vals[rng.integers(len(vals), size=(130, shape[0], shape[1]))].astype(np.int64)
+        bb = E.BatchedBoards(cfg_of(E, shape), len(b), arrays=b, key=KEY)
+        import math
+        ch = 2 ** (int(math.ceil(math.log2(shape[2]))) + 2)  # elementCrush.py:66
+        want = (b[..., None] == np.arange(ch)[None, None, None, :])  # jax.nn.one_hot: out-of-range -> zeros
+        for dt in (torch.float32, torch.uint8, torch.bfloat16, torch.float16):
+            got = bb.observe_onehot(dtype=dt)
+            assert got.shape == (len(b), shape[0], shape[1], ch)
+            assert np.array_equal(got.float().cpu().numpy(), want.astype(np.float32)), (shape, dt)
