@@ -260,7 +260,7 @@ ECG_HD int run_down(const BB<G::W> &D, int b) {
 
 // Straight-run spawns for runs of length >= 5 (mega tokens), rare.
 template <class SH>
-ECG_HD_NOINLINE void mega_spawns(Matches<typename SH::G> &m, BB<SH::G::W> L5h, BB<SH::G::W> L5v) {
+ECG_HD void mega_spawns(Matches<typename SH::G> &m, BB<SH::G::W> L5h, BB<SH::G::W> L5v) {
     using G = typename SH::G;
     while (any(L5h)) {
         const int b = pop_lowest(L5h);
@@ -277,7 +277,7 @@ ECG_HD_NOINLINE void mega_spawns(Matches<typename SH::G> &m, BB<SH::G::W> L5h, B
 // Origins that fire both a horizontal and a vertical run (L / T corner at the origin):
 // group = H cells + V cells with the origin listed twice -> never a line -> bomb.
 template <class SH>
-ECG_HD_NOINLINE void corner_spawns(Matches<typename SH::G> &m, BB<SH::G::W> K) {
+ECG_HD void corner_spawns(Matches<typename SH::G> &m, BB<SH::G::W> K) {
     using G = typename SH::G;
     while (any(K)) {
         const int b = pop_lowest(K);
@@ -293,7 +293,7 @@ ECG_HD_NOINLINE void corner_spawns(Matches<typename SH::G> &m, BB<SH::G::W> K) {
 // an earlier row (boardFunctions.py:126-131 merges the later match into the FIRST earlier
 // group sharing a cell, keeping duplicates).  Rare; kept out of line.
 template <class SH>
-ECG_HD_NOINLINE void merged_spawns(Matches<typename SH::G> &m, const BB<SH::G::W> &HO, const BB<SH::G::W> &VO,
+ECG_HD void merged_spawns(Matches<typename SH::G> &m, const BB<SH::G::W> &HO, const BB<SH::G::W> &VO,
                                    const BB<SH::G::W> &VC) {
     using G = typename SH::G;
     constexpr int W = G::W, MAXM = G::R * G::C / 3 + 1;
@@ -386,7 +386,7 @@ ECG_HD_NOINLINE void merged_spawns(Matches<typename SH::G> &m, const BB<SH::G::W
 // not in (p, e] with two equal cells below.  Carry-propagation finds p and [p, e] for all
 // segments of a row at once.
 template <class SH>
-ECG_HD_NOINLINE void scan_order_matches(Matches<typename SH::G> &m, const BB<SH::G::W> &hs, const BB<SH::G::W> &vs) {
+ECG_HD void scan_order_matches(Matches<typename SH::G> &m, const BB<SH::G::W> &hs, const BB<SH::G::W> &vs) {
     using G = typename SH::G;
     constexpr int W = G::W;
     constexpr uint32_t RM = (1u << G::C) - 1u;
@@ -454,7 +454,7 @@ ECG_HD void straight_spawn(Matches<typename SH::G> &m, int start, int n, int ste
 //   t == r, c > s : H fires from s and consumes x, so V can only start one row lower: its own group
 //                  [r+1, b] if it still has 3 cells, else the two cells below x stay.
 template <class SH>
-ECG_HD_NOINLINE void single_cross_matches(Matches<typename SH::G> &m, const BB<SH::G::W> &hs, const BB<SH::G::W> &vs,
+ECG_HD void single_cross_matches(Matches<typename SH::G> &m, const BB<SH::G::W> &hs, const BB<SH::G::W> &vs,
                                           const BB<SH::G::W> &HV3, int x) {
     using G = typename SH::G;
     constexpr int W = G::W, S = G::S;
@@ -519,6 +519,51 @@ ECG_HD_NOINLINE void single_cross_matches(Matches<typename SH::G> &m, const BB<S
     }
 }
 
+// Out-of-line entry points of the rarely taken match paths.  They take and return VALUES only: nothing of
+// the caller's register-resident state (board, Matches) ever has its address taken, so the hot loop keeps it
+// in registers and pays no local-memory traffic for the existence of these paths.
+template <class G>
+struct MatchOut {
+    BB<G::W> mask, sp, sk0, sk1;
+};
+template <class SH>
+ECG_HD_NOINLINE MatchOut<typename SH::G> crossing_matches(BB<SH::G::W> A, BB<SH::G::W> D, BB<SH::G::W> hs,
+                                                          BB<SH::G::W> vs, BB<SH::G::W> HV3, BB<SH::G::W> X) {
+    using G = typename SH::G;
+    Matches<G> m;
+    m.A = A;
+    m.D = D;
+    m.sp = bb_zero<G::W>();
+    m.sk0 = bb_zero<G::W>();
+    m.sk1 = bb_zero<G::W>();
+    if (popcount(X) == 1) single_cross_matches<SH>(m, hs, vs, HV3, pop_lowest(X));
+    else scan_order_matches<SH>(m, hs, vs);
+    MatchOut<G> o;
+    o.mask = m.mask;
+    o.sp = m.sp;
+    o.sk0 = m.sk0;
+    o.sk1 = m.sk1;
+    return o;
+}
+template <class SH>
+ECG_HD_NOINLINE MatchOut<typename SH::G> long_run_spawns(BB<SH::G::W> A, BB<SH::G::W> D, BB<SH::G::W> L5h,
+                                                         BB<SH::G::W> L5v) {
+    using G = typename SH::G;
+    Matches<G> m;
+    m.A = A;
+    m.D = D;
+    m.sp = bb_zero<G::W>();
+    m.sk0 = bb_zero<G::W>();
+    m.sk1 = bb_zero<G::W>();
+    mega_spawns<SH>(m, L5h, L5v);
+    MatchOut<G> o;
+    o.mask = bb_zero<G::W>();
+    o.sp = m.sp;
+    o.sk0 = m.sk0;
+    o.sk1 = m.sk1;
+    return o;
+}
+
 // get_matches + get_match_spawn_mask of the token board (boardFunctions.py:121-169).
 template <class SH>
 ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename SH::G> &m) {
@@ -540,12 +585,11 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
     const BB<W> V3 = vs | shl<S>(vs) | shl<2 * S>(vs);
     const BB<W> X = H3 & V3;
     if (any(X)) { // intersecting runs: the reference's result depends on scan order
-        if (popcount(X) == 1) {
-            BB<W> x1 = X;
-            single_cross_matches<SH>(m, hs, vs, H3 | V3, pop_lowest(x1));
-        } else {
-            scan_order_matches<SH>(m, hs, vs);
-        }
+        const MatchOut<G> o = crossing_matches<SH>(m.A, m.D, hs, vs, H3 | V3, X);
+        m.mask = o.mask;
+        m.sp = o.sp;
+        m.sk0 = o.sk0;
+        m.sk1 = o.sk1;
         return;
     }
     // disjoint straight runs: every maximal run is one group
@@ -556,7 +600,12 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
         const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
         add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
         add_spawn_disjoint<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
-        if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
+        if (any(L5h | L5v)) {
+            const MatchOut<G> o = long_run_spawns<SH>(m.A, m.D, L5h, L5v);
+            m.sp |= o.sp;
+            m.sk0 |= o.sk0;
+            m.sk1 |= o.sk1;
+        }
     }
 }
 
@@ -860,7 +909,7 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
 // boardFunctions.shuffle (:16-23): reseed, permute ROWS (numpy legacy Fisher-Yates), then cells
 // that held a special before the shuffle get their old value back.
 template <class SH, class RNG>
-ECG_HD_NOINLINE void shuffle_rows(Board<typename SH::G> &b, RNG &rng) {
+ECG_HD void shuffle_rows_impl(Board<typename SH::G> &b, RNG &rng) {
     using G = typename SH::G;
     constexpr int W = G::W;
     constexpr uint32_t RM = (1u << G::C) - 1u;
@@ -891,6 +940,20 @@ ECG_HD_NOINLINE void shuffle_rows(Board<typename SH::G> &b, RNG &rng) {
     }
 }
 
+template <class SH, class RNG>
+struct ShuffleOut {
+    Board<typename SH::G> b;
+    RNG rng;
+};
+template <class SH, class RNG>
+ECG_HD_NOINLINE ShuffleOut<SH, RNG> shuffle_rows(Board<typename SH::G> b, RNG rng) {
+    ShuffleOut<SH, RNG> o;
+    o.b = b;
+    o.rng = rng;
+    shuffle_rows_impl<SH>(o.b, o.rng);
+    return o;
+}
+
 struct StepOut {
     int reward;       // points of this step (boardv2.py:157-158 summed over the cascade)
     int cascades;     // iterations of the cascade loop (:138), >= 1
@@ -901,7 +964,12 @@ struct StepOut {
 // the source / target cell after the swap; `target` is the bit of the second (lower/right) cell, all regions
 // are relative to it.  Returns true when the normal get_matches path applies (:134-136).
 template <class G>
-ECG_HD_NOINLINE bool special_pair(int s1, int s2, int target, BB<G::W> &cleared) {
+struct PairOut {
+    BB<G::W> cleared;
+    bool matched;
+};
+template <class G>
+ECG_HD bool special_pair_impl(int s1, int s2, int target, BB<G::W> &cleared) {
     const int tr = target / G::S, tc = target - tr * G::S;
     const int lo = s1 < s2 ? s1 : s2, hi = s1 < s2 ? s2 : s1;
     if (hi == 4) { // a mega token is involved
@@ -920,6 +988,13 @@ ECG_HD_NOINLINE bool special_pair(int s1, int s2, int target, BB<G::W> &cleared)
         return false;
     }
     return true; // one special + plain, or two equal lines
+}
+template <class G>
+ECG_HD_NOINLINE PairOut<G> special_pair(int s1, int s2, int target) {
+    PairOut<G> o;
+    o.cleared = bb_zero<G::W>();
+    o.matched = special_pair_impl<G>(s1, s2, target, o.cleared);
+    return o;
 }
 
 // One in-flight BoardV2.apply_action (boardv2.py:43-207), cut at the cascade-loop boundary so a kernel
@@ -960,7 +1035,11 @@ ECG_HD void step_begin(Lane<SH> &L, int action) {
     L.sk0 = bb_zero<W>();
     L.sk1 = bb_zero<W>();
     L.cleared = bb_zero<W>();
-    if (s1 | s2) matched = special_pair<G>(s1, s2, b2, L.cleared);
+    if (s1 | s2) {
+        const PairOut<G> o = special_pair<G>(s1, s2, b2);
+        L.cleared = o.cleared;
+        matched = o.matched;
+    }
     if (matched) {
         const Derived<G> d = derive<SH>(bd);
         Matches<G> m;
@@ -1010,7 +1089,11 @@ ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, B
                 break;
             }
             if (shuffles == 1) rng.seek((uint32_t)(L.cascades - 1) * 2048u + 1024u);
-            shuffle_rows<SH>(bd, rng);
+            {
+                const ShuffleOut<SH, RNG> so = shuffle_rows<SH, RNG>(bd, rng);
+                bd = so.b;
+                rng = so.rng;
+            }
             d = derive<SH>(bd);
             find_matches<SH>(d, m);
             if (!m.found) legal_swaps<SH>(d, m.A, m.D, HL, VL);

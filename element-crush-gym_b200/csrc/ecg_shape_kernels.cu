@@ -292,7 +292,7 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
 }
 
 #ifndef ECG_STEP_MINB
-#define ECG_STEP_MINB 6
+#define ECG_STEP_MINB 4
 #endif
 
 struct RolloutDev {
