@@ -256,13 +256,22 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards,
 // (static, no atomics); lanes that ask in the same trip receive consecutive boards, so their 16-byte
 // chunk loads/stores stay contiguous inside the 32-board tile.
 constexpr int CHUNK = 256;
-// ECG_BLOCK_LOCKSTEP: keep the warps of a block in the same trip so they share instruction-cache lines
-#if defined(ECG_BLOCK_LOCKSTEP)
+// The lane kernel runs ONE block of LANE_BLOCK threads per SM whose warps walk the trip loop together (one
+// __syncthreads_or per trip).  The loop body is ~35 KB of SASS, more than the SM's 32 KB instruction cache; 16
+// free-running warps each streamed it on their own (stall_no_inst 56 % of stall samples, GPC instruction-fetch path
+// at 96 % of peak).  In lockstep a cache line fetched by one warp is reused by the other 15: +11 % env-steps/s
+// (4.39e9 -> 4.87e9 at 9x9x6; 128 x 4 in lockstep: 4.40e9, 256 x 2: 4.84e9, 512 x 1: 4.87e9).
+#ifndef ECG_LANE_BLOCK
+#define ECG_LANE_BLOCK 512
+#endif
+#ifndef ECG_LANE_MINB
+#define ECG_LANE_MINB 1
+#endif
+constexpr int LANE_BLOCK = ECG_LANE_BLOCK;
+#if !defined(ECG_LANE_FREE_RUNNING)
 #define ECG_TRIP_ANY(p) __syncthreads_or(p)
-#define ECG_PHASE_BARRIER() __syncthreads()
 #else
 #define ECG_TRIP_ANY(p) __any_sync(0xffffffffu, p)
-#define ECG_PHASE_BARRIER() ((void)0)
 #endif
 
 template <class SH, bool PHILOX>
@@ -291,10 +300,6 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
         if (rf.stream_pos) rf.stream_pos[i] = rpos;
 }
 
-#ifndef ECG_STEP_MINB
-#define ECG_STEP_MINB 4
-#endif
-
 struct RolloutDev {
     void *boards;
     const int32_t *moves_left;
@@ -309,14 +314,14 @@ struct RolloutDev {
 // Lane states: IDLE (needs a board) -> READY (board + legal swaps in registers, action not chosen yet)
 //              -> ACTIVE (inside the cascade loop) -> IDLE | READY (rollout: next action of the same board).
 template <class SH, bool PHILOX, bool ROLLOUT>
-__global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf, StepDev io, RolloutDev ro, int types,
+__global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillDev rf, StepDev io, RolloutDev ro, int types,
                                                                     int n) {
     using G = typename SH::G;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int IDLE = 0, READY = 1, ACTIVE = 2;
     const int lane = threadIdx.x & 31;
-    const int warp = (int)((blockIdx.x * BLOCK + threadIdx.x) >> 5);
-    const int stride = (int)((gridDim.x * BLOCK) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
+    const int warp = (int)((blockIdx.x * LANE_BLOCK + threadIdx.x) >> 5);
+    const int stride = (int)((gridDim.x * LANE_BLOCK) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
     int chunk0 = warp * CHUNK;
     int next = chunk0 < n ? chunk0 : n;
@@ -475,7 +480,6 @@ __global__ void __launch_bounds__(BLOCK, ECG_STEP_MINB) lane_kernel(RefillDev rf
                 }
             }
         }
-        ECG_PHASE_BARRIER();
     }
 }
 
@@ -540,18 +544,18 @@ unsigned persistent_grid(K kernel, long long n) {
         int dev = 0, sms = 148, per_sm = 4;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LANE_BLOCK, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
     const long long chunks = (n + CHUNK - 1) / CHUNK;
-    const long long blocks = (chunks + (BLOCK / 32) - 1) / (BLOCK / 32);
+    const long long blocks = (chunks + (LANE_BLOCK / 32) - 1) / (LANE_BLOCK / 32);
     return (unsigned)(blocks < resident ? blocks : resident);
 }
 
 template <class SH, bool PHILOX, bool ROLLOUT>
 void launch_lanes(RefillDev rf, StepDev io, RolloutDev ro, int types, long long n, cudaStream_t s) {
     lane_kernel<SH, PHILOX, ROLLOUT>
-        <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT>, n), BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
+        <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT>, n), LANE_BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
 }
 
 void op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
