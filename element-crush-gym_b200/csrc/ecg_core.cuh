@@ -721,8 +721,9 @@ template <class G>
 ECG_HD int swaps_count(const BB<G::W> &HL, const BB<G::W> &VL) {
     return popcount(HL) + popcount(VL);
 }
+// k-th legal swap (swap-bitboard order) -> bit of its source cell; vertical tells the direction
 template <class G>
-ECG_HD int swaps_select(const BB<G::W> &HL, const BB<G::W> &VL, int k) { // k-th legal swap -> action id
+ECG_HD int swaps_select_bit(const BB<G::W> &HL, const BB<G::W> &VL, int k, bool &vertical) {
     uint32_t w = 0;
     int base = 0;
     bool done = false;
@@ -751,10 +752,20 @@ ECG_HD int swaps_select(const BB<G::W> &HL, const BB<G::W> &VL, int k) { // k-th
     if (k >= c) { k -= c; pos += 2; w >>= 2; }
     if (k >= (int)(w & 1u)) pos += 1;
     int bit = base + pos;
-    const bool vertical = bit >= 32 * G::W;
+    vertical = bit >= 32 * G::W;
     if (vertical) bit -= 32 * G::W;
+    return bit;
+}
+template <class G>
+ECG_HD int action_of_swap(int bit, bool vertical) { // boardConfig.py:61-69 (encode)
     const int r = bit / G::S, col = bit - r * G::S;
     return r * G::ROWA + col + (vertical ? G::C - 1 : 0);
+}
+template <class G>
+ECG_HD int swaps_select(const BB<G::W> &HL, const BB<G::W> &VL, int k) { // k-th legal swap -> action id
+    bool vertical;
+    const int bit = swaps_select_bit<G>(HL, VL, k, vertical);
+    return action_of_swap<G>(bit, vertical);
 }
 
 // ------------------------------------------------------------------ step
@@ -1010,25 +1021,40 @@ struct Lane {
     uint32_t status;
 };
 
+// b1 = bit of the source (upper / left) cell, d = 1 (horizontal swap) or S (vertical): target = b1 + d.
 template <class SH>
-ECG_HD void step_begin(Lane<SH> &L, int action) {
+ECG_HD void step_begin_at(Lane<SH> &L, int b1, int d) {
     using G = typename SH::G;
     constexpr int W = G::W;
     Board<G> &bd = L.bd;
     L.reward = 0;
     L.cascades = 0;
     L.status = 0;
-    int b1, b2;
-    decode_action<G>(action, b1, b2); // source, target (:48)
-    { // swap (:51)
-        const BB<W> m1 = onehot<W>(b1), m2 = onehot<W>(b2), both = m1 | m2;
+    const int b2 = b1 + d;
+    int c1 = 0, c2 = 0; // cell codes of source / target AFTER the swap
+    { // swap (:51): both cells sit in the 64-bit window that starts at the word of b1
+        const int wi = b1 >> 5, s = b1 & 31;
+        const BB<W> both = onehot<W>(b1) | onehot<W>(b2);
+        uint32_t sel[W]; // all-ones for the word of b1 (AND/OR masks: a select chain over w[] would be turned into
+#pragma unroll           // a dynamically indexed local-memory array by the compiler)
+        for (int i = 0; i < W; i++) sel[i] = (i == wi) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const bool x = any(bd.p[k] & m1), y = any(bd.p[k] & m2);
-            if (x != y) bd.p[k] = bd.p[k] ^ both;
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int i = 0; i < W; i++) {
+                lo |= bd.p[k].w[i] & sel[i];
+                if (i > 0) hi |= bd.p[k].w[i] & sel[i - 1];
+            }
+            const uint32_t x = funnel_r(lo, hi, s);
+            const uint32_t v1 = x & 1u, v2 = (x >> d) & 1u; // old bits of source / target
+            c1 |= (int)(v2 << k);
+            c2 |= (int)(v1 << k);
+            const uint32_t flip = 0u - (v1 ^ v2);
+#pragma unroll
+            for (int i = 0; i < W; i++) bd.p[k].w[i] ^= both.w[i] & flip;
         }
     }
-    const int c1 = cell_code<G>(bd, b1), c2 = cell_code<G>(bd, b2);
     const int s1 = c1 >= 12 ? c1 - 11 : 0, s2 = c2 >= 12 ? c2 - 11 : 0; // 0 none, 1 h, 2 v, 3 bomb, 4 mega
     bool matched = true;
     L.sp = bb_zero<W>();
@@ -1041,14 +1067,20 @@ ECG_HD void step_begin(Lane<SH> &L, int action) {
         matched = o.matched;
     }
     if (matched) {
-        const Derived<G> d = derive<SH>(bd);
+        const Derived<G> d_ = derive<SH>(bd);
         Matches<G> m;
-        find_matches<SH>(d, m);
+        find_matches<SH>(d_, m);
         L.cleared = m.mask;
         L.sp = m.sp;
         L.sk0 = m.sk0;
         L.sk1 = m.sk1;
     }
+}
+template <class SH>
+ECG_HD void step_begin(Lane<SH> &L, int action) {
+    int b1, b2;
+    decode_action<typename SH::G>(action, b1, b2); // source, target (:48)
+    step_begin_at<SH>(L, b1, b2 - b1);
 }
 
 // One cascade iteration.  Returns true when the step is over; then HL/VL are the legal swaps of the

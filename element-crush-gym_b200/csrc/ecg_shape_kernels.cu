@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
     BB<G::W> HL, VL;
 
     for (;;) {
+#if defined(ECG_BARRIER_TOP)
+        __syncthreads();
+#endif
         // ---- cursor: idle lanes are handed the next boards
         const unsigned need = __ballot_sync(FULL, state == IDLE);
         int cand = n;
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
         if (state == READY) {
             uint32_t st = 0;
             action = -1;
+            int b1 = -1, d = 0; // Philox pick: the swap as (source bit, 1 | S), no action decode needed
             if (moves < 1) { // boardv2.py:44
                 st = ST_TERMINAL;
             } else if (!ROLLOUT && io.actions) {
@@ -421,7 +425,10 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                 if (c == 0) {
                     st = ST_NO_LEGAL;
                 } else if constexpr (PHILOX) {
-                    action = swaps_select<G>(HL, VL, (int)mulhi32(blk[0], (uint32_t)c));
+                    bool vertical;
+                    b1 = swaps_select_bit<G>(HL, VL, (int)mulhi32(blk[0], (uint32_t)c), vertical);
+                    d = vertical ? G::S : 1;
+                    action = action_of_swap<G>(b1, vertical);
                 } else { // np.random.choice(legal_actions): ascending action order, numpy's masked rejection
                     ReplayRng rng;
                     rng.init(rf.stream + (long long)src * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
@@ -434,7 +441,12 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
             }
             if (action >= 0) {
                 rpos = 0; // np.random.seed(cfg.seed) at the top of apply_action (boardv2.py:46)
-                step_begin<SH>(L, action);
+                if (b1 < 0) { // action given by the caller / replay pick: boardConfig.decode
+                    int b2;
+                    decode_action<G>(action, b1, b2);
+                    d = b2 - b1;
+                }
+                step_begin_at<SH>(L, b1, d);
                 L.status |= st;
                 moves -= 1;
                 state = ACTIVE;
