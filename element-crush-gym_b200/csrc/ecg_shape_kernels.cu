@@ -29,6 +29,18 @@ static_assert(ECG_ST_TERMINAL == ST_TERMINAL && ECG_ST_STREAM_OVERFLOW == ST_STR
 
 namespace {
 
+// Board / mask traffic uses plain (write-back) accesses: lanes of a warp finish their boards in different trips,
+// so a 32-byte sector is written 16 bytes at a time; with evict-first hints (-DECG_STREAMING_LDST: __ldcs/__stcs)
+// the halves reached HBM separately (ncu: 4.23 GB of DRAM traffic per step against 2.85 GB of buffers), with
+// write-back the L2 merges them (2.99 GB).
+#if defined(ECG_STREAMING_LDST)
+#define ECG_LD(p) __ldcs(p)
+#define ECG_ST(p, v) __stcs(p, v)
+#else
+#define ECG_LD(p) (*(p))
+#define ECG_ST(p, v) (*(p) = (v))
+#endif
+
 #ifndef ECG_BLOCK
 #define ECG_BLOCK 128
 #endif
@@ -44,7 +56,7 @@ __device__ __forceinline__ void load_board(const void *boards, long long i, Boar
     uint32_t w[BW];
 #pragma unroll
     for (int k = 0; k < CH; k++) {
-        const uint4 v = __ldcs(base + k * 32);
+        const uint4 v = ECG_LD(base + k * 32);
         w[4 * k] = v.x;
         w[4 * k + 1] = v.y;
         w[4 * k + 2] = v.z;
@@ -66,7 +78,7 @@ __device__ __forceinline__ void store_board(void *boards, long long i, const Boa
 #pragma unroll
         for (int j = 0; j < G::W; j++) w[p * G::W + j] = b.p[p].w[j];
 #pragma unroll
-    for (int k = 0; k < CH; k++) __stcs(base + k * 32, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
+    for (int k = 0; k < CH; k++) ECG_ST(base + k * 32, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
 }
 
 // packed legal mask = the two swap bitboards, HL words then VL words, tiled like the boards with 4-byte words
@@ -74,17 +86,17 @@ template <class G>
 __device__ __forceinline__ void load_mask(const uint32_t *mask, long long i, BB<G::W> &HL, BB<G::W> &VL) {
     const uint32_t *base = mask + (i >> 5) * (2 * G::W * 32) + (i & 31);
 #pragma unroll
-    for (int k = 0; k < G::W; k++) HL.w[k] = __ldcs(base + k * 32);
+    for (int k = 0; k < G::W; k++) HL.w[k] = ECG_LD(base + k * 32);
 #pragma unroll
-    for (int k = 0; k < G::W; k++) VL.w[k] = __ldcs(base + (G::W + k) * 32);
+    for (int k = 0; k < G::W; k++) VL.w[k] = ECG_LD(base + (G::W + k) * 32);
 }
 template <class G>
 __device__ __forceinline__ void store_mask(uint32_t *mask, long long i, const BB<G::W> &HL, const BB<G::W> &VL) {
     uint32_t *base = mask + (i >> 5) * (2 * G::W * 32) + (i & 31);
 #pragma unroll
-    for (int k = 0; k < G::W; k++) __stcs(base + k * 32, HL.w[k]);
+    for (int k = 0; k < G::W; k++) ECG_ST(base + k * 32, HL.w[k]);
 #pragma unroll
-    for (int k = 0; k < G::W; k++) __stcs(base + (G::W + k) * 32, VL.w[k]);
+    for (int k = 0; k < G::W; k++) ECG_ST(base + (G::W + k) * 32, VL.w[k]);
 }
 
 template <class SH>
@@ -121,9 +133,55 @@ __global__ void __launch_bounds__(BLOCK) pack_kernel(const T *__restrict__ cells
     if (status) status[i] = (uint8_t)st;
 }
 
+// board.array / the observation: one warp per tile of 32 boards.  The tile (32 x 4W words) is staged in shared
+// memory with coalesced 16-byte loads; the lanes then walk the tile's 32*R*C output cells in order, so every
+// store instruction of the warp writes one contiguous run (128 B for uint8 cells, 4 per lane; 256 B for int64).
+// `cells` must be 4-byte aligned for uint8 output (op_unpack checks and otherwise uses unpack_kernel_simple).
 template <class SH, typename T>
 __global__ void __launch_bounds__(BLOCK) unpack_kernel(const void *boards, T *__restrict__ cells, int types,
                                                        long long n) {
+    using G = typename SH::G;
+    constexpr int BW = 4 * G::W, RC = G::R * G::C, VEC = sizeof(T) == 1 ? 4 : 1;
+    static_assert((32 * RC) % VEC == 0, "tile size must be a multiple of the store width");
+    __shared__ uint32_t tile_words[BLOCK / 32][32 * BW];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long tile = (long long)blockIdx.x * (BLOCK / 32) + wib;
+    if (tile * 32 >= n) return;
+    uint32_t *tw = tile_words[wib];
+    { // chunk k of board `lane` is uint4 (tile*CH + k)*32 + lane; keep that order in shared memory
+        const uint4 *src = reinterpret_cast<const uint4 *>(boards) + tile * (BW / 4 * 32);
+#pragma unroll
+        for (int k = 0; k < BW / 4; k++) reinterpret_cast<uint4 *>(tw)[k * 32 + lane] = src[k * 32 + lane];
+    }
+    __syncwarp();
+    const CellCodec cc = make_codec(types);
+    const long long rest = n - tile * 32;
+    const int total = (int)(rest < 32 ? rest : 32) * RC; // cells of this tile
+    T *dst = cells + tile * 32 * RC;
+    for (int e0 = lane * VEC; e0 < total; e0 += 32 * VEC) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            const int e = e0 + v;
+            const int b = e / RC, idx = e - b * RC;
+            const int r = idx / G::C, c = idx - r * G::C, bit = r * G::S + c;
+            int code = 0;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const int j = p * G::W + (bit >> 5); // word j of the board = word (j & 3) of chunk (j >> 2)
+                code |= (int)((tw[((j >> 2) * 32 + b) * 4 + (j & 3)] >> (bit & 31)) & 1u) << p;
+            }
+            const int value = decode_cell(cc, code);
+            if (VEC == 1) dst[e] = (T)value;
+            else packed |= (uint32_t)value << (8 * v);
+        }
+        if (VEC == 4) *reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(dst) + e0) = packed;
+    }
+}
+
+template <class SH, typename T>
+__global__ void __launch_bounds__(BLOCK) unpack_kernel_simple(const void *boards, T *__restrict__ cells, int types,
+                                                              long long n) {
     using G = typename SH::G;
     const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
@@ -514,13 +572,17 @@ void op_pack(bool wide, const void *cells, int eb, void *boards, uint8_t *status
     }
 }
 void op_unpack(bool wide, const void *boards, void *cells, int eb, int types, long long n, cudaStream_t s) {
-    const unsigned g = grid_for(n, BLOCK);
+    const unsigned g = grid_for((n + 31) / 32, BLOCK / 32); // one warp per tile
     if (eb == 8) {
         if (wide) unpack_kernel<SHW, long long><<<g, BLOCK, 0, s>>>(boards, (long long *)cells, types, n);
         else unpack_kernel<SHN, long long><<<g, BLOCK, 0, s>>>(boards, (long long *)cells, types, n);
-    } else {
+    } else if ((reinterpret_cast<uintptr_t>(cells) & 3u) == 0) {
         if (wide) unpack_kernel<SHW, uint8_t><<<g, BLOCK, 0, s>>>(boards, (uint8_t *)cells, types, n);
         else unpack_kernel<SHN, uint8_t><<<g, BLOCK, 0, s>>>(boards, (uint8_t *)cells, types, n);
+    } else { // unaligned byte output: one thread per board
+        const unsigned g1 = grid_for(n, BLOCK);
+        if (wide) unpack_kernel_simple<SHW, uint8_t><<<g1, BLOCK, 0, s>>>(boards, (uint8_t *)cells, types, n);
+        else unpack_kernel_simple<SHN, uint8_t><<<g1, BLOCK, 0, s>>>(boards, (uint8_t *)cells, types, n);
     }
 }
 void op_unpack_mask(const uint32_t *mask, uint8_t *out, long long n, cudaStream_t s) {
