@@ -6,6 +6,8 @@ Host-side mirror of the reference interface for the hot path only:
     BatchedBoards                     N x BoardV2 in lockstep on one GPU
     Match3Env / BatchedMatch3Env      match3tile/env.py
     dist                              sharding + NCCL reduction of statistics
+    BatchedRolloutMCTS                mctslib/standard/mcts.py with GPU-batched rollouts
+    dataset / Dataset                 dataset.py (self-play samples, mirror / type-switch augmentation)
 All board logic runs in libecg.so (hand-written CUDA for sm_100a behind include/ecg.h); there is no CPU path.
 The directory name is not a Python identifier: import it with
     importlib.import_module("element-crush-gym_b200")      # or `import ecg_b200` (alias module at the repo root)
@@ -19,6 +21,8 @@ from .env import BatchedMatch3Env, HostStepper, Match3Env
 from .state import BoardV2
 from . import dist
 from .mcts import BatchedRolloutMCTS
+from . import dataset
+from .dataset import Dataset
 
 __all__ = ["BoardConfig", "BoardV2", "BatchedBoards", "BatchedMatch3Env", "Match3Env", "HostStepper", "dist",
-           "EcgError", "fresh_key", "BatchedRolloutMCTS"]
+           "EcgError", "fresh_key", "BatchedRolloutMCTS", "dataset", "Dataset"]

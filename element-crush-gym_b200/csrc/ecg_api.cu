@@ -293,6 +293,28 @@ int ecg_observe_onehot(const ecg_config *cfg, const void *boards, void *out, int
     return check_launch("ecg_observe_onehot");
 }
 
+int ecg_augment(const ecg_config *cfg, const void *boards_in, void *boards_out, int mirror, const uint8_t *type_perm,
+                int64_t n, void *stream) {
+    if (check_cfg(cfg)) return -1;
+    if (!boards_in || !boards_out) return fail("ecg_augment: NULL buffer");
+    CodeLut lut;
+    for (int c = 0; c < 16; c++) lut.v[c] = (uint8_t)c;
+    if (type_perm) { // type t (1..types) becomes type_perm[t - 1]; must be a permutation of 1..types
+        const int top = cfg->type_mask < 11 ? cfg->type_mask : 11; // plain codes the engine can hold
+        unsigned seen = 0;
+        for (int t = 1; t <= cfg->types; t++) {
+            const int v = type_perm[t - 1];
+            if (v < 1 || v > cfg->types || v > top || (seen >> v) & 1u)
+                return fail("ecg_augment: type_perm must be a permutation of 1..types");
+            seen |= 1u << v;
+            lut.v[t] = (uint8_t)v;
+        }
+    }
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->augment(boards_in, boards_out, mirror != 0, type_perm != nullptr, lut, n, (cudaStream_t)stream);
+    return check_launch("ecg_augment");
+}
+
 int ecg_episode_stats(const int32_t *score, const uint8_t *flags, int64_t *out, int64_t n, void *stream) {
     if (!score || !out) return fail("ecg_episode_stats: NULL buffer");
     if (n <= 0) return 0;

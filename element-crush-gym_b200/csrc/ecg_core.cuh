@@ -1188,6 +1188,51 @@ ECG_HD void init_board(Board<typename SH::G> &bd, uint32_t types, RNG &rng) {
     }
 }
 
+// ------------------------------------------------------------------ dataset augmentation (dataset.py:86-112)
+
+// np.fliplr(observation) (dataset.py:94): reverse the C cells of every row, plane by plane
+template <class G>
+ECG_HD Board<G> mirror_board(const Board<G> &b) {
+    constexpr uint32_t RM = (1u << G::C) - 1u;
+    Board<G> o;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        o.p[k] = bb_zero<G::W>();
+#pragma unroll
+        for (int r = 0; r < G::R; r++) {
+            const uint32_t row = extract32(b.p[k], r * G::S) & RM;
+            uint32_t rev = 0;
+#pragma unroll
+            for (int c = 0; c < G::C; c++) rev |= ((row >> c) & 1u) << (G::C - 1 - c);
+            const int b0 = r * G::S, wi = b0 >> 5, s = b0 & 31;
+#pragma unroll
+            for (int i = 0; i < G::W; i++) {
+                if (i == wi) o.p[k].w[i] |= rev << s;
+                if (i == wi + 1 && s) o.p[k].w[i] |= rev >> (32 - s);
+            }
+        }
+    }
+    return o;
+}
+
+// every cell code c becomes lut[c] (type permutation: plain codes permuted, 0 and the specials kept)
+template <class G>
+ECG_HD Board<G> remap_codes(const Board<G> &b, const uint8_t lut[16]) {
+    Board<G> o;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o.p[k] = bb_zero<G::W>();
+    for (int code = 1; code < 16; code++) { // rolled: an augmentation pass, not the step path
+        BB<G::W> m = G::valid();
+#pragma unroll
+        for (int k = 0; k < 4; k++) m = ((code >> k) & 1) ? (m & b.p[k]) : andn(m, b.p[k]);
+        const int t = lut[code];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if ((t >> k) & 1) o.p[k] |= m;
+    }
+    return o;
+}
+
 // ------------------------------------------------------------------ cell codec
 
 struct CellCodec { // boardConfig.py:29-43

@@ -27,6 +27,10 @@ struct StepDev {
     const int32_t *src_index;
 };
 
+struct CodeLut {
+    uint8_t v[16];
+};
+
 // `wide` selects the types >= 8 instantiation (4 token planes + np.clip(.., 0, 32) quirk)
 struct ShapeOps {
     void (*pack)(bool wide, const void *cells, int elem_bytes, void *boards, uint8_t *status, int types, long long n,
@@ -43,6 +47,8 @@ struct ShapeOps {
                     long long *total_reward, int32_t *steps_done, uint8_t *status, int types, long long n,
                     cudaStream_t s);
     void (*onehot)(const void *boards, void *out, int channels, int elem_kind, int types, long long n, cudaStream_t s);
+    void (*augment)(const void *boards_in, void *boards_out, bool mirror, bool remap, CodeLut lut, long long n,
+                    cudaStream_t s);
 };
 
 const ShapeOps *shape_ops_5();

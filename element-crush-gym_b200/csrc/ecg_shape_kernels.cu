@@ -235,6 +235,20 @@ __global__ void __launch_bounds__(BLOCK) onehot_kernel(const void *boards, T *__
     for (int k = 0; k < channels; k++) dst[k] = k == value ? one : (T)0;
 }
 
+// dataset augmentation (dataset.py:86-112, 114-176): mirrored and / or type-permuted copies of packed boards
+template <class SH>
+__global__ void __launch_bounds__(BLOCK) augment_kernel(const void *boards_in, void *boards_out, bool mirror, bool remap,
+                                                        CodeLut lut, long long n) {
+    using G = typename SH::G;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    Board<G> b;
+    load_board<G>(boards_in, i, b);
+    if (mirror) b = mirror_board<G>(b);
+    if (remap) b = remap_codes<G>(b, lut.v);
+    store_board<G>(boards_out, i, b);
+}
+
 template <class SH>
 __global__ void __launch_bounds__(BLOCK) legal_kernel(const void *boards, uint32_t *mask, long long n) {
     using G = typename SH::G;
@@ -663,8 +677,13 @@ void op_onehot(const void *boards, void *out, int channels, int elem_kind, int t
                                                           (uint16_t)(elem_kind == 2 ? 0x3F80 : 0x3C00), types, n);
 }
 
+void op_augment(const void *boards_in, void *boards_out, bool mirror, bool remap, CodeLut lut, long long n,
+                cudaStream_t s) {
+    augment_kernel<SHN><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(boards_in, boards_out, mirror, remap, lut, n);
+}
+
 const ShapeOps k_ops = {op_pack, op_unpack, op_unpack_mask, op_init, op_legal, op_random_action, op_step, op_rollout,
-                        op_onehot};
+                        op_onehot, op_augment};
 
 } // namespace
 

@@ -132,6 +132,7 @@ class BatchedRolloutMCTS:
             node = self._root
         action, best_child = max(self._root.children.items(), key=lambda kv: kv[1].visits)
         policies = self._root.policies
+        self.last_root_actions = list(self._root.children.keys())  # the action behind each entry of `policies`
         node = self._root
         while not node.state.is_terminal and node.is_fully_expanded:
             node = node.best_child(0)

@@ -147,6 +147,14 @@ int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const
 int ecg_observe_onehot(const ecg_config *cfg, const void *boards, void *out, int channels, int elem_kind, int64_t n,
                        void *stream);
 
+/* Dataset augmentation (dataset.py:86-112 mirror, :114-176 type_switch) on packed boards: boards_out[i] =
+ * fliplr(boards_in[i]) when mirror != 0, and every plain token t (1..types) renamed to type_perm[t-1] when
+ * type_perm (HOST pointer, a permutation of 1..types) is not NULL; empty cells and special tokens keep their
+ * value.  boards_out may alias boards_in.  The matching policy re-indexing (action -> mirrored action,
+ * dataset.py:99-107) is a fixed permutation of the action ids and lives in the host layer. */
+int ecg_augment(const ecg_config *cfg, const void *boards_in, void *boards_out, int mirror, const uint8_t *type_perm,
+                int64_t n, void *stream);
+
 /* episode statistics (main.py:240-267 sample()): out[0]=sum(score) out[1]=n out[2]=min out[3]=max
  * out[4]=#flags&WON out[5]=sum(score^2); out must be zero-initialised except out[2]=INT64_MAX, out[3]=INT64_MIN */
 int ecg_episode_stats(const int32_t *score, const uint8_t *flags, int64_t *out, int64_t n, void *stream);
