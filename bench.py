@@ -287,10 +287,12 @@ def run_ours(args):
             "config": workload(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
-                         "kernel": "lane_kernel<Shape<9,9,3,false>, philox, step> (persistent warp loop)",
+                         "kernel": "lane_kernel<Shape<9,9,3,false>, philox, step> (persistent warp loop, one 512-thread "
+                                   "block per SM in trip lockstep)",
                          "algorithmic_bytes_per_launch": BYTES_PER_STEP * n, "avg_launch_ms": avg_launch_ms,
                          "peak_source": peak_src,
-                         "note": "instruction-supply/integer bound, not HBM bound (DESIGN.md section 5): ~2400 integer thread-instructions per env-step against 117 B"},
+                         "note": "integer-ALU-pipe bound, not HBM bound (DESIGN.md section 5): ~1700 integer "
+                                 "thread-instructions per env-step against 117 B; ncu: ALU pipe 66 % of peak, DRAM 11 %"},
             "cpu_baseline": cpu,
             "run": {"mean_cascades_per_step": mean_casc, "boards_without_legal_move": stuck, "boards_flagged": bad,
                     "episode_stats": stats},
