@@ -46,6 +46,14 @@ ECG_HD int ctz32(uint32_t x) {
     return __builtin_ctz(x);
 #endif
 }
+// 1 + index of the highest set bit; 0 for x == 0
+ECG_HD int bitlen32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return 32 - __clz((int)x);
+#else
+    return x ? 32 - __builtin_clz(x) : 0;
+#endif
+}
 ECG_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -210,6 +218,22 @@ ECG_HD uint32_t extract32(const BB<W> &a, int b) {
         hi = (i == wi + 1) ? a.w[i] : hi;
     }
     return funnel_r(lo, hi, s);
+}
+// bit i of the result = a(i*S + c), i < R: column c of a board-shaped bitboard as a dense word
+template <int R, int S, int W>
+ECG_HD uint32_t column_bits(const BB<W> &a, int c) {
+    uint32_t sh[W]; // a >> c (c < 32)
+#pragma unroll
+    for (int i = 0; i < W; i++) sh[i] = funnel_r(a.w[i], i + 1 < W ? a.w[i + 1 < W ? i + 1 : 0] : 0u, c);
+    uint32_t col = 0;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int bp = (i * S) & 31, wi = (i * S) >> 5; // compile-time after unrolling
+        col |= (bp >= i ? sh[wi] >> (bp - i) : sh[wi] << (i - bp)) & (1u << i);
+    }
+    return col;
 }
 // a << j for a run-time 0 <= j < 32
 template <int W>

@@ -459,64 +459,74 @@ ECG_HD void single_cross_matches(Matches<typename SH::G> &m, const BB<SH::G::W> 
     using G = typename SH::G;
     constexpr int W = G::W, S = G::S;
     const int r = x / S, c = x - r * S;
-    const uint32_t Ar = extract32(m.A, r * S) & ((1u << G::C) - 1u);
+    // H = [s, e] in row r and V = [t, b] in column c from the dense row word of A and column word of D
+    // (A is zero in the last column and the pad column, D in the last row: the chains end by themselves)
+    const uint32_t Ar = extract32(m.A, r * S);
+    const uint32_t Dc = column_bits<G::R, S>(m.D, c);
     const int e = c + ctz32(~(Ar >> c));
-    int s = c;
-    while (s > 0 && ((Ar >> (s - 1)) & 1u)) s--;
-    int t = r, b = r;
-    while (t > 0 && testbit(m.D, (t - 1) * S + c)) t--;
-    while (testbit(m.D, b * S + c)) b++;
+    const int s = bitlen32(~Ar & ((1u << c) - 1u)); // one past the highest A == 0 left of c
+    const int b = r + ctz32(~(Dc >> r));
+    const int t = bitlen32(~Dc & ((1u << r) - 1u));
     const int hl = e - s + 1, vl = b - t + 1;
-    const BB<W> Hm = bitrange<W>(r * S + s, r * S + e + 1);
-    const BB<W> Vm = shl_rt(G::col0(), c) & bitrange<W>(t * S, (b + 1) * S);
-    // all other runs: disjoint maximal runs, one group each (same formulas as the intersection-free case)
-    m.mask = andn(HV3, Hm | Vm);
-    const BB<W> L4h = andn(andn(hs, shl<1>(m.A)) & shr<2>(m.A), Hm);
-    const BB<W> L4v = andn(andn(vs, shl<S>(m.D)) & shr<2 * S>(m.D), Vm);
-    if (any(L4h | L4v)) {
-        const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
-        add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
-        add_spawn_disjoint<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
-        if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
+    m.mask = HV3;
+    // every run other than H and V is disjoint from both and forms its own group: the formulas of the
+    // intersection-free case, with the run starts of H and V taken out; skipped when H and V are all there is
+    if (popcount(HV3) != hl + vl - 1) {
+        const BB<W> own = onehot<W>(r * S + s) | onehot<W>(t * S + c);
+        const BB<W> L4h = andn(andn(hs, shl<1>(m.A)) & shr<2>(m.A), own);
+        const BB<W> L4v = andn(andn(vs, shl<S>(m.D)) & shr<2 * S>(m.D), own);
+        if (any(L4h | L4v)) {
+            const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
+            add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
+            add_spawn_disjoint<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
+            if (any(L5h | L5v)) mega_spawns<SH>(m, L5h, L5v);
+        }
     }
     // groups are created in scan order; the pair's groups may be created between the others', but spawn
-    // centres of disjoint groups never coincide, so the order of the add_spawn calls is irrelevant here
+    // centres of disjoint groups never coincide, so the order of the add_spawn calls is irrelevant here.
+    // Each case ends in at most one spawn (start cell, run length, step) or one bomb cell, and at most one
+    // pair of cells (first, first + gap) that stays on the board.
+    int bomb = -1, st0 = 0, stn = 0, stp = 1, keep = -1, gap = 1;
     if (t < r) {
         if (c != s) { // merged T / + shape
-            m.mask |= Hm | Vm;
             const int a = r - t; // vertical cells above row r
-            int idx = (hl + vl) / 2, centre;
+            int idx = (hl + vl) / 2;
             if (idx < a) {
-                centre = (t + idx) * S + c;
+                bomb = (t + idx) * S + c;
             } else if (idx - a < hl + 1) { // row r holds s..c, c, c+1..e
                 idx -= a;
-                centre = r * S + (idx <= c - s ? s + idx : s + idx - 1);
+                bomb = r * S + (idx <= c - s ? s + idx : s + idx - 1);
             } else {
-                centre = (r + 1 + (idx - a - (hl + 1))) * S + c;
+                bomb = (r + 1 + (idx - a - (hl + 1))) * S + c;
             }
-            add_spawn_disjoint<SH>(m, onehot<W>(centre), K_BOMB);
-        } else {
-            m.mask |= Vm;
-            straight_spawn<SH>(m, t * S + c, vl, S);
-            if (hl >= 4) {
-                m.mask |= Hm;
+        } else { // V is its own group; H can only fire from s + 1
+            st0 = t * S + c;
+            stn = vl;
+            stp = S;
+            if (hl >= 4) { // two straight groups: the second one spawns here, the first one below
                 straight_spawn<SH>(m, r * S + s + 1, hl - 1, 1);
+            } else {
+                keep = x + 1;
             }
         }
     } else {
         if (c == s) { // corner at the origin: (r,c),(r,c),(r,c+1)..(r,e),(r+1,c)..(b,c)
-            m.mask |= Hm | Vm;
             const int idx = (hl + vl) / 2;
-            add_spawn_disjoint<SH>(m, onehot<W>(idx <= hl ? x + idx - 1 : x + (idx - hl) * S), K_BOMB);
-        } else {
-            m.mask |= Hm;
-            straight_spawn<SH>(m, r * S + s, hl, 1);
+            bomb = idx <= hl ? x + idx - 1 : x + (idx - hl) * S;
+        } else { // H is its own group; V can only start one row lower
+            st0 = r * S + s;
+            stn = hl;
             if (vl >= 4) {
-                m.mask |= Vm;
                 straight_spawn<SH>(m, (r + 1) * S + c, vl - 1, S);
+            } else {
+                keep = x + S;
+                gap = S;
             }
         }
     }
+    if (bomb >= 0) add_spawn_disjoint<SH>(m, onehot<W>(bomb), K_BOMB);
+    straight_spawn<SH>(m, st0, stn, stp);
+    if (keep >= 0) m.mask = andn(m.mask, onehot<W>(keep) | onehot<W>(keep + gap));
 }
 
 // Out-of-line entry points of the rarely taken match paths.  They take and return VALUES only: nothing of
