@@ -610,11 +610,15 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
         const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
         add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
         add_spawn_disjoint<SH>(m, shl<2 * S>(andn(L4v, L5v)), K_HLINE);
-        if (any(L5h | L5v)) {
-            const MatchOut<G> o = long_run_spawns<SH>(m.A, m.D, L5h, L5v);
-            m.sp |= o.sp;
-            m.sk0 |= o.sk0;
-            m.sk1 |= o.sk1;
+        if (any(L5h | L5v)) { // runs of exactly 5: mega token on the third cell; longer ones out of line
+            const BB<W> L6h = L5h & shr<4>(m.A), L6v = L5v & shr<4 * S>(m.D);
+            add_spawn_disjoint<SH>(m, shl<2>(andn(L5h, L6h)) | shl<2 * S>(andn(L5v, L6v)), K_MEGA);
+            if (any(L6h | L6v)) {
+                const MatchOut<G> o = long_run_spawns<SH>(m.A, m.D, L6h, L6v);
+                m.sp |= o.sp;
+                m.sk0 |= o.sk0;
+                m.sk1 |= o.sk1;
+            }
         }
     }
 }
@@ -857,7 +861,9 @@ ECG_HD BB<SH::G::W> trigger_specials(const Board<typename SH::G> &bd, const BB<S
     using G = typename SH::G;
     constexpr int W = G::W;
     const BB<W> k0 = bd.p[0] & spec, k1 = bd.p[1] & spec;
-    BB<W> z = fill_rows_with_any<G>(andn(andn(spec, k0), k1)); // h_line: its row (:147-148)
+    const BB<W> hl = andn(andn(spec, k0), k1);
+    BB<W> z = bb_zero<W>();
+    if (any(hl)) z = fill_rows_with_any<G>(hl); // h_line: its row (:147-148)
     const BB<W> vl = andn(k0, k1);
     if (any(vl)) z |= fill_cols_with_any<G>(vl);               // v_line: its column (:149-150)
     BB<W> bombs = andn(k1, k0);
@@ -892,6 +898,19 @@ ECG_PHASE void gravity(Board<G> &b) {
     }
 }
 
+// plane |= bit when (v & M): one predicate-setting LOP3 and one predicated LOP3 (the compiler's own branch-free
+// form is shift, arithmetic shift, and, add)
+template <uint32_t M>
+ECG_HD void deposit_bit(uint32_t &plane, uint32_t v, uint32_t bit) {
+#if defined(__CUDA_ARCH__) && !defined(ECG_NO_PRED_DEPOSIT)
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 q, t, 0;\n\t@q or.b32 %0, %0, %3;\n\t}"
+        : "+r"(plane)
+        : "r"(v), "n"(M), "r"(bit));
+#else
+    if (v & M) plane |= bit;
+#endif
+}
+
 // refill (boardv2.py:172-173).  Replay: the reference's order (columns left to right, first draw =
 // topmost hole).  Philox: holes in bit (row-major) order, draws addressed per cascade iteration.
 template <class SH, class RNG>
@@ -907,11 +926,10 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
                 const uint32_t bit = h & (0u - h);
                 h ^= bit;
                 const uint32_t v = 1u + rng.digit(types);
-                // the cell is empty, so adding the bit is OR-ing it (IMAD keeps the logic pipe free)
-                b.p[0].w[w] += bit * (v & 1u);
-                b.p[1].w[w] += bit * ((v >> 1) & 1u);
-                b.p[2].w[w] += bit * ((v >> 2) & 1u);
-                if (SH::TPL > 3) b.p[3].w[w] += bit * (v >> 3);
+                deposit_bit<1>(b.p[0].w[w], v, bit);
+                deposit_bit<2>(b.p[1].w[w], v, bit);
+                deposit_bit<4>(b.p[2].w[w], v, bit);
+                if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[w], v, bit);
             }
         }
     } else {

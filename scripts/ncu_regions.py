@@ -5,12 +5,36 @@ ecg_shape_kernels.cu (the inlined bit-board helpers of ecg_bits.cuh carry no con
 grouped into the regions below.  Usage: scripts/ncu_regions.py report.ncu-rep n_boards"""
 import bisect, collections, csv, io, re, subprocess, sys
 
-REGIONS = [  # (name, file, first line, last line) in ecg_core.cuh ("K" = ecg_shape_kernels.cu)
-    ("philox", "core", 34, 131), ("spawn helpers / crossing", "core", 227, 566), ("find_matches", "core", 567, 611),
-    ("legal_swaps", "core", 612, 655), ("pick / select", "core", 656, 800), ("trigger_specials", "core", 801, 865),
-    ("gravity", "core", 866, 884), ("refill", "core", 885, 965), ("shuffle", "core", 966, 1015),
-    ("special_pair", "core", 1016, 1055), ("step_begin (swap)", "core", 1056, 1125), ("step_iter", "core", 1126, 1200),
-]
+import os
+
+CORE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "element-crush-gym_b200", "csrc", "ecg_core.cuh")
+GROUPS = {  # function of ecg_core.cuh -> region (anything else keeps its own name)
+    "philox4x32_10": "philox", "init": "philox / digits", "u32": "philox / digits", "digit": "philox / digits",
+    "below": "philox / digits", "seek": "philox / digits", "preset_block": "philox / digits",
+    "philox_pick": "philox", "derive": "find_matches", "eq_at": "find_matches", "add_spawn": "crossing / rare spawns",
+    "add_spawn_disjoint": "find_matches", "run_right": "crossing / rare spawns", "run_down": "crossing / rare spawns",
+    "mega_spawns": "crossing / rare spawns", "corner_spawns": "crossing / rare spawns",
+    "merged_spawns": "crossing / rare spawns", "scan_order_matches": "crossing / rare spawns",
+    "straight_spawn": "crossing / rare spawns", "single_cross_matches": "crossing / rare spawns",
+    "crossing_matches": "crossing / rare spawns", "long_run_spawns": "crossing / rare spawns",
+    "swaps_to_actions": "pick / select", "mask_count": "pick / select", "mask_select": "pick / select",
+    "swaps_count": "pick / select", "swaps_select_bit": "pick / select", "action_of_swap": "pick / select",
+    "swaps_select": "pick / select", "decode_action": "pick / select", "fill_rows_with_any": "trigger_specials",
+    "fill_cols_with_any": "trigger_specials", "shuffle_rows_impl": "shuffle", "shuffle_rows": "shuffle",
+    "special_pair_impl": "special_pair", "step_begin_at": "swap (step_begin)", "step_begin": "swap (step_begin)",
+    "step_iter": "step_iter (clear, points, glue)",
+}
+
+
+def core_functions():
+    """[(first line, name)] of the functions defined in ecg_core.cuh, in file order"""
+    out = []
+    pat = re.compile(r"^\s*(?:ECG_\w+|static|inline)\b[^;=]*?\b(\w+)\s*\([^;]*$")
+    for i, line in enumerate(open(CORE), 1):
+        m = pat.match(line)
+        if m and not line.lstrip().startswith("//"):
+            out.append((i, m.group(1)))
+    return out
 
 
 def export(rep, what):
@@ -60,6 +84,8 @@ def main():
         v[2] += int(r[isamp] or 0)
         v[3] += 1
     byline = "--lines" in sys.argv
+    funcs = core_functions()
+    starts = [f[0] for f in funcs]
     out = collections.defaultdict(lambda: [0, 0, 0, 0])
     for (f, line), v in agg.items():
         if byline:
@@ -67,7 +93,9 @@ def main():
         elif f == "ecg_shape_kernels.cu":
             key = "kernel glue (cursor, load/store, state machine)"
         else:
-            key = next((nm for nm, _, lo, hi in REGIONS if lo <= line <= hi), f"core:{line}")
+            k = bisect.bisect_right(starts, line) - 1
+            fn = funcs[k][1] if k >= 0 else f"core:{line}"
+            key = GROUPS.get(fn, fn)
         for i in range(4):
             out[key][i] += v[i]
     tot = [sum(v[i] for v in out.values()) for i in range(4)]
