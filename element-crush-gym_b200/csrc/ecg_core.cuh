@@ -594,6 +594,7 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
     const BB<W> H3 = hs | shl<1>(hs) | shl<2>(hs);
     const BB<W> V3 = vs | shl<S>(vs) | shl<2 * S>(vs);
     const BB<W> X = H3 & V3;
+#if !defined(ECG_PROBE_NOCROSS) // perf probe only (wrong results): what do the rare match paths cost?
     if (any(X)) { // intersecting runs: the reference's result depends on scan order
         const MatchOut<G> o = crossing_matches<SH>(m.A, m.D, hs, vs, H3 | V3, X);
         m.mask = o.mask;
@@ -602,6 +603,7 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
         m.sk1 = o.sk1;
         return;
     }
+#endif
     // disjoint straight runs: every maximal run is one group
     m.mask = H3 | V3;
     const BB<W> L4h = andn(hs, shl<1>(m.A)) & shr<2>(m.A); // run starts with >= 4 cells

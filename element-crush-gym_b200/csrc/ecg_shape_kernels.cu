@@ -327,7 +327,10 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards,
 // Boards are handed out in chunks of CHUNK consecutive boards; warp w owns chunks w, w + nwarps, ...
 // (static, no atomics); lanes that ask in the same trip receive consecutive boards, so their 16-byte
 // chunk loads/stores stay contiguous inside the 32-board tile.
-constexpr int CHUNK = 256;
+#ifndef ECG_CHUNK
+#define ECG_CHUNK 256
+#endif
+constexpr int CHUNK = ECG_CHUNK;
 // The lane kernel runs ONE block of LANE_BLOCK threads per SM whose warps walk the trip loop together (one
 // __syncthreads_or per trip).  The loop body is ~35 KB of SASS, more than the SM's 32 KB instruction cache; 16
 // free-running warps each streamed it on their own (stall_no_inst 56 % of stall samples, GPC instruction-fetch path
