@@ -40,7 +40,8 @@ class StepIO(C.Structure):
                 ("mask_in", C.c_void_p), ("actions_out", C.c_void_p), ("moves_left", C.c_void_p),
                 ("reward", C.c_void_p), ("score", C.c_void_p), ("cascades", C.c_void_p),
                 ("mask_out", C.c_void_p), ("flags", C.c_void_p), ("status", C.c_void_p),
-                ("env_goal", C.c_int32), ("reserved", C.c_int32), ("src_index", C.c_void_p)]
+                ("env_goal", C.c_int32), ("reserved", C.c_int32), ("src_index", C.c_void_p),
+                ("scratch", C.c_void_p)]
 
 
 EXPORTS = {

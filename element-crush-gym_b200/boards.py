@@ -8,6 +8,7 @@ board logic runs in the CUDA kernels behind the C-ABI (include/ecg.h).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import secrets
 
 import torch
@@ -68,6 +69,9 @@ class BatchedBoards:
         self.flags = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.status = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.last_actions = torch.full((self.n,), -1, dtype=torch.int32, device=dev)
+        # work list of the two-kernel Philox step (ecg_step_io.scratch); ECG_SINGLE_KERNEL=1 keeps the one-kernel step
+        self.two_kernel_step = refill == "philox" and os.environ.get("ECG_SINGLE_KERNEL", "0") != "1"
+        self._scratch = torch.empty(self.n + 1, dtype=torch.int32, device=dev) if self.two_kernel_step else None
         if _empty:
             return
         if refill == "replay":
@@ -197,6 +201,8 @@ class BatchedBoards:
         io.flags = self.flags.data_ptr()
         io.status = self.status.data_ptr()
         io.env_goal = self.env_goal
+        if self._scratch is not None:
+            io.scratch = self._scratch.data_ptr()
         rf = self._refill()
         N.check(self.L.ecg_step(C.byref(self.nat), C.byref(rf), C.byref(io), self.n, _stream(self.device)), "ecg_step")
         self._mask_valid = True

@@ -267,7 +267,12 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
     sd.env_goal = io->env_goal;
     sd.types = cfg->types;
     sd.src_index = io->src_index;
-    ops_for(cfg->rows)->step(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), sd, n, (cudaStream_t)stream);
+    sd.handoff = io->scratch;
+    sd.jobs = nullptr;
+    sd.n_jobs = nullptr;
+    const int launched =
+        ops_for(cfg->rows)->step(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), sd, n, (cudaStream_t)stream);
+    g_launches.fetch_add(launched - 1, std::memory_order_relaxed);
     return check_launch("ecg_step");
 }
 

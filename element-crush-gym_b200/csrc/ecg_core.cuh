@@ -53,6 +53,18 @@ ECG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     out[3] = c3;
 }
 
+// Out-of-line copy for the rare block fetches inside loops (a refill of more than 12 tiles, shuffles): values in,
+// values out, so the callers' state stays in registers and the loops carry no inlined Philox rounds.
+struct PhiloxBlock {
+    uint32_t w[4];
+};
+template <int UNUSED = 0> // a template only so that the header can define it
+ECG_HD_NOINLINE PhiloxBlock philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    PhiloxBlock b;
+    philox4x32_10(c0, c1, c2, c3, k0, k1, b.w);
+    return b;
+}
+
 // Throughput mode: bounded ints by multiply-high of one u32 (no rejection).
 // Draw addressing inside the (board, step) substream (engine-defined; mirrored by the oracle's Philox mode):
 //   word 0: the random action pick of this step (philox_pick);
@@ -97,7 +109,11 @@ struct PhiloxRng {
         const uint32_t k = pos++;
         const uint32_t b = k >> 2;
         if (b != blk_idx) {
-            philox4x32_10(b, step, b0, b1, k0, k1, blk);
+            const PhiloxBlock nb = philox_block(b, step, b0, b1, k0, k1);
+            blk[0] = nb.w[0];
+            blk[1] = nb.w[1];
+            blk[2] = nb.w[2];
+            blk[3] = nb.w[3];
             blk_idx = b;
         }
         const uint32_t j = k & 3u;
@@ -222,6 +238,7 @@ struct Matches {
     BB<G::W> sk0, sk1;   // spawn kind bits
     BB<G::W> A, D;       // eq-right / eq-down of the analysed board (reused by legal_mask)
     bool found;
+    bool rare;           // find_matches<SH, true> only: a rare case was met and nothing was computed (see there)
 };
 
 template <class SH>
@@ -575,7 +592,11 @@ ECG_HD_NOINLINE MatchOut<typename SH::G> long_run_spawns(BB<SH::G::W> A, BB<SH::
 }
 
 // get_matches + get_match_spawn_mask of the token board (boardFunctions.py:121-169).
-template <class SH>
+// FAST = true is the common-case build used by the first of the two step kernels (ecg_shape_kernels.cu): the two
+// rare cases -- a horizontal and a vertical run share a cell (scan-order dependent result, 1.4 % of the calls), or
+// a run of 6 or more -- are not computed; m.rare is set instead (m.found is true) and the caller hands the board
+// over to the exact kernel.  Their code (2 000 instructions) then never enters the hot kernel's instruction stream.
+template <class SH, bool FAST = false>
 ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename SH::G> &m) {
     using G = typename SH::G;
     constexpr int W = G::W, S = G::S;
@@ -584,6 +605,7 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
     m.sp = bb_zero<W>();
     m.sk0 = bb_zero<W>();
     m.sk1 = bb_zero<W>();
+    m.rare = false;
     const BB<W> hs = m.A & shr<1>(m.A); // b, b+1, b+2 equal
     const BB<W> vs = m.D & shr<S>(m.D);
     m.found = any(hs | vs);
@@ -594,8 +616,32 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
     const BB<W> H3 = hs | shl<1>(hs) | shl<2>(hs);
     const BB<W> V3 = vs | shl<S>(vs) | shl<2 * S>(vs);
     const BB<W> X = H3 & V3;
-#if !defined(ECG_PROBE_NOCROSS) // perf probe only (wrong results): what do the rare match paths cost?
+    const BB<W> L4h = andn(hs, shl<1>(m.A)) & shr<2>(m.A); // run starts with >= 4 cells
+    const BB<W> L4v = andn(vs, shl<S>(m.D)) & shr<2 * S>(m.D);
     if (any(X)) { // intersecting runs: the reference's result depends on scan order
+        if constexpr (FAST) {
+            // Two thirds of these calls are ONE shared cell x on a board whose runs are all plain triples:
+            // single_cross_matches with hl == vl == 3 and no other spawn collapses to four cases.
+            //   x top of V and left end of H (corner)   : everything cleared, bomb on the right end of H
+            //   x top of V, not left end (H fires first): the two cells below x stay
+            //   x left end, not top (V fires first)     : the two cells right of x stay
+            //   neither (merged T / + shape)            : everything cleared, bomb on x -- or on the cell left
+            //                                             of x when x is the bottom of V and the right end of H
+            if (popcount(X) != 1 || any(L4h | L4v)) {
+                m.rare = true;
+                m.mask = bb_zero<W>();
+                return;
+            }
+            const bool top = any(andn(X, shl<S>(m.D))), left = any(andn(X, shl<1>(m.A)));
+            BB<W> keep = bb_zero<W>(), bomb = bb_zero<W>();
+            if (top && !left) keep = shl<S>(X) | shl<2 * S>(X);
+            if (!top && left) keep = shl<1>(X) | shl<2>(X);
+            if (top && left) bomb = shl<2>(X);
+            if (!top && !left) bomb = any(X & (m.A | m.D)) ? X : shr<1>(X);
+            m.mask = andn(H3 | V3, keep);
+            add_spawn_disjoint<SH>(m, bomb, K_BOMB);
+            return;
+        }
         const MatchOut<G> o = crossing_matches<SH>(m.A, m.D, hs, vs, H3 | V3, X);
         m.mask = o.mask;
         m.sp = o.sp;
@@ -603,11 +649,8 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
         m.sk1 = o.sk1;
         return;
     }
-#endif
     // disjoint straight runs: every maximal run is one group
     m.mask = H3 | V3;
-    const BB<W> L4h = andn(hs, shl<1>(m.A)) & shr<2>(m.A); // run starts with >= 4 cells
-    const BB<W> L4v = andn(vs, shl<S>(m.D)) & shr<2 * S>(m.D);
     if (any(L4h | L4v)) {
         const BB<W> L5h = L4h & shr<3>(m.A), L5v = L4v & shr<3 * S>(m.D);
         add_spawn_disjoint<SH>(m, shl<2>(andn(L4h, L5h)), K_VLINE);
@@ -616,6 +659,10 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
             const BB<W> L6h = L5h & shr<4>(m.A), L6v = L5v & shr<4 * S>(m.D);
             add_spawn_disjoint<SH>(m, shl<2>(andn(L5h, L6h)) | shl<2 * S>(andn(L5v, L6v)), K_MEGA);
             if (any(L6h | L6v)) {
+                if constexpr (FAST) {
+                    m.rare = true;
+                    return;
+                }
                 const MatchOut<G> o = long_run_spawns<SH>(m.A, m.D, L6h, L6v);
                 m.sp |= o.sp;
                 m.sk0 |= o.sk0;
@@ -1052,8 +1099,11 @@ struct Lane {
 };
 
 // b1 = bit of the source (upper / left) cell, d = 1 (horizontal swap) or S (vertical): target = b1 + d.
-template <class SH>
-ECG_HD void step_begin_at(Lane<SH> &L, int b1, int d) {
+// FAST = true (see find_matches): returns true, with L half-updated, when the step needs the exact build -- a
+// swap of two special tokens, or a rare match case; the caller drops L and steps the board again from its
+// unchanged input with FAST = false.
+template <class SH, bool FAST = false>
+ECG_HD bool step_begin_at(Lane<SH> &L, int b1, int d) {
     using G = typename SH::G;
     constexpr int W = G::W;
     Board<G> &bd = L.bd;
@@ -1092,6 +1142,7 @@ ECG_HD void step_begin_at(Lane<SH> &L, int b1, int d) {
     L.sk1 = bb_zero<W>();
     L.cleared = bb_zero<W>();
     if (s1 | s2) {
+        if constexpr (FAST) return true;
         const PairOut<G> o = special_pair<G>(s1, s2, b2);
         L.cleared = o.cleared;
         matched = o.matched;
@@ -1099,12 +1150,14 @@ ECG_HD void step_begin_at(Lane<SH> &L, int b1, int d) {
     if (matched) {
         const Derived<G> d_ = derive<SH>(bd);
         Matches<G> m;
-        find_matches<SH>(d_, m);
+        find_matches<SH, FAST>(d_, m);
+        if (FAST && m.rare) return true;
         L.cleared = m.mask;
         L.sp = m.sp;
         L.sk0 = m.sk0;
         L.sk1 = m.sk1;
     }
+    return false;
 }
 template <class SH>
 ECG_HD void step_begin(Lane<SH> &L, int action) {
@@ -1115,11 +1168,14 @@ ECG_HD void step_begin(Lane<SH> &L, int action) {
 
 // One cascade iteration.  Returns true when the step is over; then HL/VL are the legal swaps of the
 // final board (the reference computes legal_actions there too, :188, to decide about shuffling).
-template <class SH, class RNG>
-ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+// FAST = true (see find_matches): `rare` is set (and false returned) when the iteration needs the exact build:
+// a rare match case, or a final board without a legal swap (the shuffle loop).
+template <class SH, class RNG, bool FAST>
+ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, BB<SH::G::W> &VL, bool &rare) {
     using G = typename SH::G;
     constexpr int W = G::W;
     Board<G> &bd = L.bd;
+    rare = false;
     L.cascades++;
     { // :141-163 trigger pass, points, clear, spawn, clip
         const BB<W> spec = bd.p[3] & bd.p[2];
@@ -1140,25 +1196,35 @@ ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, B
     refill<SH>(bd, rng, types, L.cascades - 1); // :172-173
     Derived<G> d = derive<SH>(bd);
     Matches<G> m;
-    find_matches<SH>(d, m); // :181
+    find_matches<SH, FAST>(d, m); // :181
+    if (FAST && m.rare) {
+        rare = true;
+        return false;
+    }
     bool done = false;
     if (!m.found) {
         legal_swaps<SH>(d, m.A, m.D, HL, VL);
-        int shuffles = 0;
-        while (!m.found && !any(HL | VL)) { // :188-194
-            if (shuffles++ >= SHUFFLE_CAP) {
-                L.status |= ST_SHUFFLE_CAP;
-                break;
+        if (FAST && !any(HL | VL)) {
+            rare = true;
+            return false;
+        }
+        if constexpr (!FAST) {
+            int shuffles = 0;
+            while (!m.found && !any(HL | VL)) { // :188-194
+                if (shuffles++ >= SHUFFLE_CAP) {
+                    L.status |= ST_SHUFFLE_CAP;
+                    break;
+                }
+                if (shuffles == 1) rng.seek((uint32_t)(L.cascades - 1) * 2048u + 1024u);
+                {
+                    const ShuffleOut<SH, RNG> so = shuffle_rows<SH, RNG>(bd, rng);
+                    bd = so.b;
+                    rng = so.rng;
+                }
+                d = derive<SH>(bd);
+                find_matches<SH>(d, m);
+                if (!m.found) legal_swaps<SH>(d, m.A, m.D, HL, VL);
             }
-            if (shuffles == 1) rng.seek((uint32_t)(L.cascades - 1) * 2048u + 1024u);
-            {
-                const ShuffleOut<SH, RNG> so = shuffle_rows<SH, RNG>(bd, rng);
-                bd = so.b;
-                rng = so.rng;
-            }
-            d = derive<SH>(bd);
-            find_matches<SH>(d, m);
-            if (!m.found) legal_swaps<SH>(d, m.A, m.D, HL, VL);
         }
         done = !m.found; // :195
     }
@@ -1177,6 +1243,12 @@ ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, B
     return done;
 }
 
+template <class SH, class RNG>
+ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    bool rare;
+    return step_iter<SH, RNG, false>(L, rng, types, HL, VL, rare);
+}
+
 // BoardV2.apply_action (boardv2.py:43-207) minus the terminal test, run to completion.
 template <class SH, class RNG>
 ECG_HD void step_board(Board<typename SH::G> &bd, int action, uint32_t types, RNG &rng, StepOut &out,
@@ -1191,6 +1263,32 @@ ECG_HD void step_board(Board<typename SH::G> &bd, int action, uint32_t types, RN
     out.reward = L.reward;
     out.cascades = L.cascades;
     out.status = L.status;
+}
+
+// The two-kernel step on one board: the common-case build first, the exact build from the unchanged input when it
+// hands the board off.  Host tests use it to fuzz the FAST logic against the oracle; returns true on a hand-off.
+template <class SH, class RNG>
+ECG_HD bool step_board_two_pass(Board<typename SH::G> &bd, int action, uint32_t types, RNG &rng, StepOut &out,
+                                BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    const RNG rng0 = rng;
+    Lane<SH> L;
+    L.bd = bd;
+    rng.reseed();
+    int b1, b2;
+    decode_action<typename SH::G>(action, b1, b2);
+    bool rare = step_begin_at<SH, true>(L, b1, b2 - b1);
+    while (!rare && !step_iter<SH, RNG, true>(L, rng, types, HL, VL, rare)) {
+    }
+    if (rare) {
+        rng = rng0;
+        step_board<SH>(bd, action, types, rng, out, HL, VL);
+        return true;
+    }
+    bd = L.bd;
+    out.reward = L.reward;
+    out.cascades = L.cascades;
+    out.status = L.status;
+    return false;
 }
 
 // BoardV2.__init__ (boardv2.py:20-27): draw a board, redraw matched cells until clean.

@@ -25,6 +25,10 @@ struct StepDev {
     uint8_t *flags, *status;
     int env_goal, types;
     const int32_t *src_index;
+    // two-kernel step (ecg_step_io.scratch): the common-case kernel appends the jobs it hands off to
+    // handoff[1 + handoff[0]++]; the exact kernel then runs over jobs[0 .. *n_jobs)
+    int32_t *handoff;
+    const int32_t *jobs, *n_jobs;
 };
 
 struct CodeLut {
@@ -42,7 +46,7 @@ struct ShapeOps {
     void (*legal)(bool wide, const void *boards, uint32_t *mask, long long n, cudaStream_t s);
     void (*random_action)(bool philox, RefillDev rf, const uint32_t *mask, int32_t *actions, uint8_t *status,
                           long long n, cudaStream_t s);
-    void (*step)(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s);
+    int (*step)(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s); // kernels launched
     void (*rollout)(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left,
                     long long *total_reward, int32_t *steps_done, uint8_t *status, int types, long long n,
                     cudaStream_t s);

@@ -324,13 +324,13 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards,
 // runs a small state machine: FETCH a board (load, choose the action, swap, first match pass), then one
 // cascade ITERATION per trip of the warp loop, then FINISH (legal mask, stores) and fetch the next board
 // in the same trip.  Every trip therefore runs one cascade iteration on (almost) all 32 lanes.
-// Boards are handed out in chunks of CHUNK consecutive boards; warp w owns chunks w, w + nwarps, ...
+// Boards are handed out in chunks of CHUNK_BOARDS consecutive boards; warp w owns chunks w, w + nwarps, ...
 // (static, no atomics); lanes that ask in the same trip receive consecutive boards, so their 16-byte
 // chunk loads/stores stay contiguous inside the 32-board tile.
 #ifndef ECG_CHUNK
 #define ECG_CHUNK 256
 #endif
-constexpr int CHUNK = ECG_CHUNK;
+constexpr int CHUNK_BOARDS = ECG_CHUNK;
 // The lane kernel runs ONE block of LANE_BLOCK threads per SM whose warps walk the trip loop together (one
 // __syncthreads_or per trip).  The loop body is ~35 KB of SASS, more than the SM's 32 KB instruction cache; 16
 // free-running warps each streamed it on their own (stall_no_inst 56 % of stall samples, GPC instruction-fetch path
@@ -388,14 +388,26 @@ struct RolloutDev {
 // until moves_left reaches 0; only the final board and the collected reward go back to HBM).
 // Lane states: IDLE (needs a board) -> READY (board + legal swaps in registers, action not chosen yet)
 //              -> ACTIVE (inside the cascade loop) -> IDLE | READY (rollout: next action of the same board).
-template <class SH, bool PHILOX, bool ROLLOUT>
+//
+// FAST = true is the first kernel of a two-kernel step (StepDev::handoff): the common-case build of the board logic
+// (find_matches<SH, true>: no intersecting runs, no run of 6+, no swap of two specials, no shuffle).  A lane that
+// meets one of those drops its board -- nothing of it has been written -- and appends the job to the hand-off list;
+// the exact kernel (FAST = false, launched right after on the same stream) steps those boards from their unchanged
+// inputs.  Without the rare paths the trip body fits the SM's instruction cache, so the FAST kernel's warps run
+// free (no trip barrier); the exact kernel keeps the one-barrier-per-trip lockstep described above.
+template <class SH, bool PHILOX, bool ROLLOUT, bool FAST>
 __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillDev rf, StepDev io, RolloutDev ro, int types,
                                                                     int n) {
     using G = typename SH::G;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int IDLE = 0, READY = 1, ACTIVE = 2;
+    static_assert(!(FAST && ROLLOUT), "the hand-off is per step");
+    if constexpr (!FAST && !ROLLOUT)
+        if (io.n_jobs) n = *io.n_jobs;
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * LANE_BLOCK + threadIdx.x) >> 5);
+    // the job list of a two-kernel step is short (5 % of the boards): small chunks spread it over all warps
+    const int CHUNK = (!FAST && !ROLLOUT && io.n_jobs) ? 32 : ::CHUNK_BOARDS;
     const int stride = (int)((gridDim.x * LANE_BLOCK) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
     int chunk0 = warp * CHUNK;
@@ -449,6 +461,8 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
         // ---- LOAD: IDLE -> READY
         if (state == IDLE && cand < n) {
             idx = cand;
+            if constexpr (!FAST && !ROLLOUT)
+                if (io.jobs) idx = io.jobs[cand];
             src = idx;
             if constexpr (!ROLLOUT)
                 if (io.src_index) src = io.src_index[idx];
@@ -483,6 +497,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
             }
         }
         // ---- BEGIN: READY -> ACTIVE: choose the action, swap, first match pass
+        bool handoff = false; // FAST: this lane's board goes to the exact kernel
         if (state == READY) {
             uint32_t st = 0;
             action = -1;
@@ -521,10 +536,10 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                     decode_action<G>(action, b1, b2);
                     d = b2 - b1;
                 }
-                step_begin_at<SH>(L, b1, d);
+                handoff = step_begin_at<SH, FAST>(L, b1, d);
                 L.status |= st;
                 moves -= 1;
-                state = ACTIVE;
+                state = handoff ? IDLE : ACTIVE;
             } else if constexpr (ROLLOUT) { // the episode is over (terminal, or nothing legal)
                 if (st != ST_TERMINAL) st_acc |= st;
                 store_board<G>(ro.boards, idx, L.bd);
@@ -540,7 +555,13 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                 state = IDLE;
             }
         }
-        if (!ECG_TRIP_ANY(state != IDLE)) break;
+        if constexpr (FAST) { // a board dropped in this trip is still to be appended to the hand-off list below
+            if (!__any_sync(FULL, state != IDLE || handoff)) break;
+        } else {
+            if (!ROLLOUT && io.n_jobs) { // the short job list of a two-kernel step: too few trips to pay for barriers
+                if (!__any_sync(FULL, state != IDLE)) break;
+            } else if (!ECG_TRIP_ANY(state != IDLE)) break;
+        }
         // ---- ITERATE: one cascade iteration on every active lane; FINISH the steps whose cascade ended
         if (state == ACTIVE) {
             typename RngOf<PHILOX>::type rng;
@@ -550,8 +571,9 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
             } else {
                 rng.init(rf.stream + (long long)src * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
             }
-            const bool fin = step_iter<SH>(L, rng, (uint32_t)types, HL, VL);
+            const bool fin = step_iter<SH, typename RngOf<PHILOX>::type, FAST>(L, rng, (uint32_t)types, HL, VL, handoff);
             if constexpr (!PHILOX) rpos = rng.pos;
+            if (FAST && handoff) state = IDLE;
             if (fin) {
                 if constexpr (ROLLOUT) {
                     total += L.reward;
@@ -565,6 +587,15 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                                              HL, VL, rpos);
                     state = IDLE;
                 }
+            }
+        }
+        if constexpr (FAST) { // hand the dropped boards over (idx is still this trip's board)
+            const unsigned hm = __ballot_sync(FULL, handoff);
+            if (hm) {
+                int base = 0;
+                if (lane == __ffs((int)hm) - 1) base = atomicAdd(io.handoff, __popc(hm));
+                base = __shfl_sync(FULL, base, __ffs((int)hm) - 1);
+                if (handoff) io.handoff[1 + base + __popc(hm & ((1u << lane) - 1u))] = idx;
             }
         }
     }
@@ -638,19 +669,39 @@ unsigned persistent_grid(K kernel, long long n) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LANE_BLOCK, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const long long chunks = (n + CHUNK - 1) / CHUNK;
+    const long long chunks = (n + CHUNK_BOARDS - 1) / CHUNK_BOARDS;
     const long long blocks = (chunks + (LANE_BLOCK / 32) - 1) / (LANE_BLOCK / 32);
     return (unsigned)(blocks < resident ? blocks : resident);
 }
 
-template <class SH, bool PHILOX, bool ROLLOUT>
+template <class SH, bool PHILOX, bool ROLLOUT, bool FAST = false>
 void launch_lanes(RefillDev rf, StepDev io, RolloutDev ro, int types, long long n, cudaStream_t s) {
-    lane_kernel<SH, PHILOX, ROLLOUT>
-        <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT>, n), LANE_BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
+    lane_kernel<SH, PHILOX, ROLLOUT, FAST>
+        <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT, FAST>, n), LANE_BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
 }
 
-void op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
+// Philox mode with a hand-off list: the common-case kernel over all boards, then the exact kernel over the jobs it
+// handed off (their number is read on the device: no host synchronisation in between)
+template <class SH>
+void launch_two_kernel_step(RefillDev rf, StepDev io, long long n, cudaStream_t s) {
     const RolloutDev ro = {};
+    cudaMemsetAsync(io.handoff, 0, sizeof(int32_t), s);
+    launch_lanes<SH, true, false, true>(rf, io, ro, io.types, n, s);
+    StepDev io2 = io;
+    io2.jobs = io.handoff + 1;
+    io2.n_jobs = io.handoff;
+    io2.handoff = nullptr;
+    launch_lanes<SH, true, false, false>(rf, io2, ro, io.types, n, s);
+}
+
+int op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
+    const RolloutDev ro = {};
+    if (philox && io.handoff) {
+        if (wide) launch_two_kernel_step<SHW>(rf, io, n, s);
+        else launch_two_kernel_step<SHN>(rf, io, n, s);
+        return 2;
+    }
+    io.handoff = nullptr;
     if (wide) {
         if (philox) launch_lanes<SHW, true, false>(rf, io, ro, io.types, n, s);
         else launch_lanes<SHW, false, false>(rf, io, ro, io.types, n, s);
@@ -658,6 +709,7 @@ void op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cuda
         if (philox) launch_lanes<SHN, true, false>(rf, io, ro, io.types, n, s);
         else launch_lanes<SHN, false, false>(rf, io, ro, io.types, n, s);
     }
+    return 1;
 }
 void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left, long long *total_reward,
                 int32_t *steps_done, uint8_t *status, int types, long long n, cudaStream_t s) {

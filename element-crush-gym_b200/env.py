@@ -113,6 +113,8 @@ class HostStepper:
         self.h_flags = torch.zeros(n, dtype=torch.uint8, **pin)
         self.d_actions = torch.zeros(n, dtype=torch.int32, device=dev)
         self.d_obs = torch.zeros((n, R, Cc), dtype=torch.uint8, device=dev)
+        self.scratch = (torch.empty(n + len(self.bounds), dtype=torch.int32, device=dev)
+                        if env.board.two_kernel_step else None)
         self.h2d_bytes = n * 4
         self.d2h_bytes = n * (R * Cc + 4 + 1)
 
@@ -135,6 +137,8 @@ class HostStepper:
         io.flags = b.flags[lo:].data_ptr()
         io.status = b.status[lo:].data_ptr()
         io.env_goal = b.env_goal
+        if self.scratch is not None:  # k-th chunk [lo, hi): hi - lo + 1 entries of the work list from lo + k
+            io.scratch = self.scratch[lo + self.bounds.index((lo, hi)):].data_ptr()
         rf = b._refill()
         rf.board0 = b.board0 + lo
         if b.refill_mode == "replay":

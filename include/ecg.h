@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ECG_VERSION 101
+#define ECG_VERSION 102
 
 /* per-board status bits */
 #define ECG_ST_TERMINAL 1        /* n_actions < 1: board returned unchanged (boardv2.py:44-45) */
@@ -91,6 +91,11 @@ typedef struct ecg_step_io {
                                  refill stream / Philox id, moves_left, score, mask_in) and writes every output at i:
                                  "expand these (board, action) pairs" = Node.expand / greedy_action (boardv2.py:209-218,
                                  mctslib/standard/mcts.py:31-42).  Needs boards_out != boards_in. */
+    int32_t *scratch;        /* optional work list, [n + 1] int32, contents irrelevant on entry and exit.  Philox mode
+                                only: when given, the step runs as TWO kernels -- the common-case kernel over all n
+                                boards, which hands the boards that need a rare path (intersecting runs, runs of 6+,
+                                a swap of two special tokens, the shuffle loop; about 5 % of the 9x9x6 steps) over to
+                                the exact kernel through this list.  Results are identical with and without it. */
 } ecg_step_io;
 
 int ecg_version(void);

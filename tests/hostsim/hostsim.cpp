@@ -53,6 +53,7 @@ struct StepArgs {
     int32_t *cascades;
     uint8_t *status, *legal;
     int64_t n;
+    int64_t *handoffs; // modes 3 / 4: incremented per board the common-case build handed off
 };
 
 template <class SH>
@@ -71,14 +72,24 @@ static void step_t(const StepArgs &a) {
             so.status = terminal ? ST_TERMINAL : ST_BAD_ACTION;
             Derived<G> d = derive<SH>(b);
             legal_swaps<SH>(d, eq_at<SH, 1>(d), eq_at<SH, G::S>(d), HL, VL);
-        } else if (a.mode == 2) {
+        } else if (a.mode == 2 || a.mode == 4) { // mode + 2: common-case build first, exact build on a hand-off
             PhiloxRng rng;
             rng.init(a.key, a.board0 + (uint64_t)i, a.step_ctr);
-            step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+            if (a.mode == 4) {
+                if (step_board_two_pass<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL) && a.handoffs)
+                    ++*a.handoffs;
+            } else {
+                step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+            }
         } else {
             ReplayRng rng;
             rng.init(a.raw + i * a.raw_stride, (uint32_t)a.raw_len, 0);
-            step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+            if (a.mode == 3) {
+                if (step_board_two_pass<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL) && a.handoffs)
+                    ++*a.handoffs;
+            } else {
+                step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+            }
         }
         unpack_board<SH>(cc, b, a.out + i * N);
         if (a.reward) a.reward[i] = so.reward;
@@ -163,6 +174,8 @@ static void init_t(int types, const uint32_t *raw, int64_t raw_stride, int64_t r
         }                                                                                \
     } while (0)
 
+static int64_t g_handoffs = 0;
+
 extern "C" {
 
 int hs_step(int rows, int cols, int types, int mode, const uint32_t *raw, int64_t raw_stride, int64_t raw_len,
@@ -170,10 +183,14 @@ int hs_step(int rows, int cols, int types, int mode, const uint32_t *raw, int64_
             const int32_t *moves_left, int64_t *out, int64_t *reward, int32_t *cascades, uint8_t *status,
             uint8_t *legal, int64_t n) {
     if (rows != cols || types < 1 || types > 11) return -1;
+    g_handoffs = 0;
     StepArgs a = {types, mode, raw, raw_stride, raw_len, key, board0, step_ctr, in, actions, moves_left,
-                  out, reward, cascades, status, legal, n};
+                  out, reward, cascades, status, legal, n, &g_handoffs};
     DISPATCH(rows, types, step_t<SH>(a));
 }
+
+// boards the common-case build handed off in the last hs_step call (modes 3 / 4)
+int64_t hs_handoffs(void) { return g_handoffs; }
 
 int hs_legal(int rows, int cols, int types, const int64_t *boards, uint8_t *legal, int64_t n) {
     if (rows != cols || types < 1 || types > 11) return -1;

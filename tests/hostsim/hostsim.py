@@ -40,11 +40,12 @@ class HostSim:
         self.A = rows * (cols - 1) * 2
         self.L = lib()
 
-    def step(self, boards, actions, *, mode, raw=None, key=0, board0=0, step_ctr=0, moves_left=None):
+    def step(self, boards, actions, *, mode, raw=None, key=0, board0=0, step_ctr=0, moves_left=None, two_pass=False):
+        """two_pass: the two-kernel step on the host -- common-case build first, exact build on a hand-off"""
         boards = np.ascontiguousarray(boards, dtype=np.int64)
         n = boards.shape[0]
         actions = np.ascontiguousarray(actions, dtype=np.int32)
-        m = {"replay": 1, "philox": 2}[mode]
+        m = {"replay": 1, "philox": 2}[mode] + (2 if two_pass else 0)
         stride = rawlen = 0
         if raw is not None:
             raw = np.ascontiguousarray(raw, dtype=np.uint32)
@@ -59,7 +60,9 @@ class HostSim:
                             C.c_uint64(key), C.c_uint64(board0), C.c_uint32(step_ctr), _p(boards), _p(actions), _p(ml),
                             _p(out), _p(reward), _p(casc), _p(status), _p(legal), C.c_int64(n))
         assert rc == 0
-        return {"boards": out, "reward": reward, "cascades": casc, "status": status, "legal": legal.astype(bool)}
+        self.L.hs_handoffs.restype = C.c_int64
+        return {"boards": out, "reward": reward, "cascades": casc, "status": status, "legal": legal.astype(bool),
+                "handoffs": int(self.L.hs_handoffs())}
 
     def legal(self, boards):
         boards = np.ascontiguousarray(boards, dtype=np.int64)

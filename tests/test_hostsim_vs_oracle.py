@@ -127,6 +127,33 @@ def test_fuzz_dense_boards_philox(shape):
     rh = h.step(b, acts, mode="philox", key=KEY, board0=77, step_ctr=5)
     for k in ("boards", "reward", "cascades", "status", "legal"):
         assert np.array_equal(ro[k], rh[k]), k
+    # the two-kernel step: common-case build (find_matches<SH, true>), exact build for the boards it hands off
+    r2 = h.step(b, acts, mode="philox", key=KEY, board0=77, step_ctr=5, two_pass=True)
+    for k in ("boards", "reward", "cascades", "status", "legal"):
+        assert np.array_equal(ro[k], r2[k]), k
+    assert 0 < r2["handoffs"] < n  # both builds were exercised
+
+
+@pytest.mark.parametrize("shape", [(9, 9, 6), (6, 6, 4), (12, 12, 7)])
+def test_two_pass_episodes_philox(shape):
+    """Natural play (random legal actions from fresh boards, 12 steps): most single crossings are plain triples,
+    which the common-case build resolves in closed form instead of handing them off."""
+    o, h = Oracle(*shape), HostSim(*shape)
+    n = 1500
+    b, _ = h.init(mode="philox", n=n, key=KEY)
+    rng = np.random.default_rng(7)
+    handoffs = 0
+    for step in range(12):
+        lo = o.legal_mask_batch(b)
+        acts = np.array([rng.choice(np.flatnonzero(m)) if m.any() else 0 for m in lo], dtype=np.int32)
+        ro = o.step_batch(b, acts, mode="philox", key=KEY, board0=0, step_ctr=step)
+        r2 = h.step(b, acts, mode="philox", key=KEY, board0=0, step_ctr=step, two_pass=True)
+        for k in ("boards", "reward", "cascades", "status", "legal"):
+            assert np.array_equal(ro[k], r2[k]), (k, step)
+        handoffs += r2["handoffs"]
+        b = ro["boards"]
+    print("hand-off rate %dx%dx%d: %.2f %%" % (*shape, 100.0 * handoffs / (n * 12)))
+    assert 0 < handoffs < (0.04 if shape == (9, 9, 6) else 0.25) * n * 12
 
 
 def test_caps_and_flags():
