@@ -353,7 +353,8 @@ template <class SH, bool PHILOX>
 __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev &io, long long i, long long src,
                                              const Board<typename SH::G> &b, bool stepped, int action, int moves,
                                              int reward, int cascades, uint32_t status, const BB<SH::G::W> &HL,
-                                             const BB<SH::G::W> &VL, uint32_t rpos) {
+                                             const BB<SH::G::W> &VL, uint32_t rpos, int score_in = 0,
+                                             bool have_score = false) {
     using G = typename SH::G;
     if (stepped || io.boards_out != io.boards_in) store_board<G>(io.boards_out, i, b);
     if (io.mask_out) store_mask<G>(io.mask_out, i, HL, VL);
@@ -362,7 +363,7 @@ __device__ __forceinline__ void finish_board(const RefillDev &rf, const StepDev 
     if (io.reward) io.reward[i] = reward;
     int score = reward;
     if (io.score) {
-        score += io.score[src];
+        score += have_score ? score_in : io.score[src];
         io.score[i] = score;
     }
     if (io.cascades) io.cascades[i] = cascades;
@@ -424,6 +425,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
     long long total = 0;         // rollout: points collected so far
     int steps_done = 0;
     uint32_t st_acc = 0;
+    int score_in = 0; // FAST: the board's score, loaded with the board
     BB<G::W> HL, VL;
 
     for (;;) {
@@ -458,6 +460,23 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                 next += cnt;
             }
         }
+        if constexpr (FAST) {
+            // free-running warps: pull the lines of the boards this warp hands out next into L1 one trip ahead
+            const int pf = next + lane;
+            if (need && pf < end && !io.src_index) {
+                constexpr int CH = G::W;
+                const uint4 *bp = reinterpret_cast<const uint4 *>(io.boards_in) + (long long)(pf >> 5) * (CH * 32) + (pf & 31);
+#pragma unroll
+                for (int k = 0; k < CH; k++) asm volatile("prefetch.global.L1 [%0];" ::"l"(bp + k * 32));
+                if (!io.actions)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(io.mask_in + (long long)(pf >> 5) * (2 * G::W * 32) +
+                                                                   (lane % (2 * G::W)) * 32 + (pf & 31)));
+                else
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(io.actions + pf));
+                if (io.moves_left) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.moves_left + pf));
+                if (io.score) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.score + pf));
+            }
+        }
         // ---- LOAD: IDLE -> READY
         if (state == IDLE && cand < n) {
             idx = cand;
@@ -480,6 +499,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                 load_board<G>(io.boards_in, src, L.bd);
                 moves = io.moves_left ? io.moves_left[src] : 1;
                 if (!io.actions) load_mask<G>(io.mask_in, src, HL, VL);
+                if constexpr (FAST) score_in = io.score ? io.score[src] : 0; // registers to spare: no load at FINISH
             }
             state = READY;
         }
@@ -551,7 +571,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                 state = IDLE;
             } else { // no-op boards are finished on the spot
                 if (io.mask_out) legal_of<SH>(L.bd, HL, VL);
-                finish_board<SH, PHILOX>(rf, io, idx, src, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos);
+                finish_board<SH, PHILOX>(rf, io, idx, src, L.bd, false, -1, moves, 0, 0, st, HL, VL, rpos, score_in, FAST);
                 state = IDLE;
             }
         }
@@ -584,7 +604,7 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
                     state = READY; // next action of this board (or the end of the episode)
                 } else {
                     finish_board<SH, PHILOX>(rf, io, idx, src, L.bd, true, action, moves, L.reward, L.cascades, L.status,
-                                             HL, VL, rpos);
+                                             HL, VL, rpos, score_in, FAST);
                     state = IDLE;
                 }
             }
