@@ -61,6 +61,7 @@ EXPORTS = {
     "ecg_random_action": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p]),
     "ecg_step": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.POINTER(StepIO), C.c_int64, C.c_void_p]),
+    "ecg_step_mark_event": (C.c_int, [C.c_void_p]),
     "ecg_rollout": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_episode_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

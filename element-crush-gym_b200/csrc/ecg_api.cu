@@ -22,6 +22,7 @@ namespace {
 
 thread_local char g_err[256] = "";
 std::atomic<long long> g_launches{0};
+thread_local void *g_mid_event = nullptr; // ecg_step_mark_event
 
 int fail(const char *msg) {
     snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -243,6 +244,11 @@ int ecg_random_action(const ecg_config *cfg, const ecg_refill *rf, const uint32_
     return check_launch("ecg_random_action");
 }
 
+int ecg_step_mark_event(void *event) {
+    g_mid_event = event;
+    return 0;
+}
+
 int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io, int64_t n, void *stream) {
     if (check_cfg(cfg) || check_refill(rf)) return -1;
     if (!io || !io->boards_in || !io->boards_out) return fail("ecg_step: boards_in/boards_out are required");
@@ -270,6 +276,8 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
     sd.handoff = io->scratch;
     sd.jobs = nullptr;
     sd.n_jobs = nullptr;
+    sd.mid_event = g_mid_event;
+    g_mid_event = nullptr;
     const int launched =
         ops_for(cfg->rows)->step(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), sd, n, (cudaStream_t)stream);
     g_launches.fetch_add(launched - 1, std::memory_order_relaxed);

@@ -29,6 +29,7 @@ struct StepDev {
     // handoff[1 + handoff[0]++]; the exact kernel then runs over jobs[0 .. *n_jobs)
     int32_t *handoff;
     const int32_t *jobs, *n_jobs;
+    void *mid_event; // host side only: cudaEvent_t recorded between the two kernels (ecg_step_mark_event)
 };
 
 struct CodeLut {

@@ -707,6 +707,7 @@ void launch_two_kernel_step(RefillDev rf, StepDev io, long long n, cudaStream_t 
     const RolloutDev ro = {};
     cudaMemsetAsync(io.handoff, 0, sizeof(int32_t), s);
     launch_lanes<SH, true, false, true>(rf, io, ro, io.types, n, s);
+    if (io.mid_event) cudaEventRecord((cudaEvent_t)io.mid_event, s);
     StepDev io2 = io;
     io2.jobs = io.handoff + 1;
     io2.n_jobs = io.handoff;

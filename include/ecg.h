@@ -139,6 +139,9 @@ int ecg_random_action(const ecg_config *cfg, const ecg_refill *rf, const uint32_
 
 /* BoardV2.apply_action (boardv2.py:43-207) + Match3Env.step bookkeeping (env.py:48-56) for n boards */
 int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io, int64_t n, void *stream);
+/* Measurement hook: the next two-kernel ecg_step of this thread records `event` (a cudaEvent_t) on its stream
+ * between the common-case kernel and the exact kernel, so a caller can time the two separately (bench.py). */
+int ecg_step_mark_event(void *event);
 
 /* MCTS.rollout / random_task (mctslib/standard/mcts.py:14-19, samplerTasks.py:9-14): play random legal
  * actions until moves_left reaches 0.  boards are updated in place; total_reward[n] receives the points
