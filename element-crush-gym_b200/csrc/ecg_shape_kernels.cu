@@ -343,6 +343,13 @@ constexpr int CHUNK_BOARDS = ECG_CHUNK;
 #define ECG_LANE_MINB 1
 #endif
 constexpr int LANE_BLOCK = ECG_LANE_BLOCK;
+// The common-case kernel fits 96 registers per thread, i.e. 640-thread blocks (20 warps per SM instead of 16), but
+// measures the same with them (6.47e9 vs 6.46e9 env-steps/s): it is issue bound, not latency bound.  576 threads
+// (18 warps, uneven over the 4 sub-partitions) are 9 % slower.
+#ifndef ECG_FAST_BLOCK
+#define ECG_FAST_BLOCK 512
+#endif
+__host__ __device__ constexpr int lane_block(bool fast) { return fast ? ECG_FAST_BLOCK : LANE_BLOCK; }
 #if !defined(ECG_LANE_FREE_RUNNING)
 #define ECG_TRIP_ANY(p) __syncthreads_or(p)
 #else
@@ -397,7 +404,7 @@ struct RolloutDev {
 // inputs.  Without the rare paths the trip body fits the SM's instruction cache, so the FAST kernel's warps run
 // free (no trip barrier); the exact kernel keeps the one-barrier-per-trip lockstep described above.
 template <class SH, bool PHILOX, bool ROLLOUT, bool FAST>
-__global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillDev rf, StepDev io, RolloutDev ro, int types,
+__global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(RefillDev rf, StepDev io, RolloutDev ro, int types,
                                                                     int n) {
     using G = typename SH::G;
     constexpr unsigned FULL = 0xffffffffu;
@@ -406,10 +413,10 @@ __global__ void __launch_bounds__(LANE_BLOCK, ECG_LANE_MINB) lane_kernel(RefillD
     if constexpr (!FAST && !ROLLOUT)
         if (io.n_jobs) n = *io.n_jobs;
     const int lane = threadIdx.x & 31;
-    const int warp = (int)((blockIdx.x * LANE_BLOCK + threadIdx.x) >> 5);
+    const int warp = (int)((blockIdx.x * lane_block(FAST) + threadIdx.x) >> 5);
     // the job list of a two-kernel step is short (5 % of the boards): small chunks spread it over all warps
     const int CHUNK = (!FAST && !ROLLOUT && io.n_jobs) ? 32 : ::CHUNK_BOARDS;
-    const int stride = (int)((gridDim.x * LANE_BLOCK) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
+    const int stride = (int)((gridDim.x * lane_block(FAST)) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
     int chunk0 = warp * CHUNK;
     int next = chunk0 < n ? chunk0 : n;
@@ -680,24 +687,25 @@ void op_random_action(bool philox, RefillDev rf, const uint32_t *mask, int32_t *
 }
 // persistent grid: all resident warps, but no more than there are chunks
 template <class K>
-unsigned persistent_grid(K kernel, long long n) {
+unsigned persistent_grid(K kernel, long long n, int block) {
     static int resident = 0; // per kernel instantiation
     if (resident == 0) {
         int dev = 0, sms = 148, per_sm = 4;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LANE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
     const long long chunks = (n + CHUNK_BOARDS - 1) / CHUNK_BOARDS;
-    const long long blocks = (chunks + (LANE_BLOCK / 32) - 1) / (LANE_BLOCK / 32);
+    const long long blocks = (chunks + (block / 32) - 1) / (block / 32);
     return (unsigned)(blocks < resident ? blocks : resident);
 }
 
 template <class SH, bool PHILOX, bool ROLLOUT, bool FAST = false>
 void launch_lanes(RefillDev rf, StepDev io, RolloutDev ro, int types, long long n, cudaStream_t s) {
+    constexpr int B = lane_block(FAST);
     lane_kernel<SH, PHILOX, ROLLOUT, FAST>
-        <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT, FAST>, n), LANE_BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
+        <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT, FAST>, n, B), B, 0, s>>>(rf, io, ro, types, (int)n);
 }
 
 // Philox mode with a hand-off list: the common-case kernel over all boards, then the exact kernel over the jobs it
