@@ -271,7 +271,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             a = hs.random_action()          # D2H: 4 B/board
-            hs.step(a)                      # H2D: 4 B/board; D2H: obs 81 + reward 4 + flags 1 B/board
+            hs.step(a)                      # H2D: 4 B/board; D2H: obs 81 + reward 4 + done 1 + won 1 B/board
         torch.cuda.synchronize(dev)
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()

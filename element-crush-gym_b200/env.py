@@ -110,13 +110,18 @@ class HostStepper:
         self.h_actions = torch.zeros(n, dtype=torch.int32, **pin)
         self.h_obs = torch.zeros((n, R, Cc), dtype=torch.uint8, **pin)
         self.h_reward = torch.zeros(n, dtype=torch.int32, **pin)
-        self.h_flags = torch.zeros(n, dtype=torch.uint8, **pin)
+        self.h_done = torch.zeros(n, dtype=torch.bool, **pin)
+        self.h_won = torch.zeros(n, dtype=torch.bool, **pin)
         self.d_actions = torch.zeros(n, dtype=torch.int32, device=dev)
         self.d_obs = torch.zeros((n, R, Cc), dtype=torch.uint8, device=dev)
+        # done / won as 0/1 bytes, split from the flags byte on the device: a host-side pass over N flags per step would
+        # cost more than the copy (and torchrun pins the host side to one thread)
+        self.d_done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.d_won = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.scratch = (torch.empty(n + len(self.bounds), dtype=torch.int32, device=dev)
                         if env.board.two_kernel_step else None)
         self.h2d_bytes = n * 4
-        self.d2h_bytes = n * (R * Cc + 4 + 1)
+        self.d2h_bytes = n * (R * Cc + 4 + 2)
 
     def _chunk_call(self, lo, hi, fn_step):
         import ctypes as C
@@ -165,14 +170,16 @@ class HostStepper:
                                      C.c_void_p(self.d_obs[lo:].data_ptr()), 1, hi - lo, sp), "ecg_unpack")
                 self.h_obs[lo:hi].copy_(self.d_obs[lo:hi], non_blocking=True)
                 self.h_reward[lo:hi].copy_(b.step_reward[lo:hi], non_blocking=True)
-                self.h_flags[lo:hi].copy_(b.flags[lo:hi], non_blocking=True)
+                torch.bitwise_and(b.flags[lo:hi], N.FLAG_DONE, out=self.d_done[lo:hi])
+                torch.bitwise_right_shift(b.flags[lo:hi], 1, out=self.d_won[lo:hi])  # FLAG_WON == 2, the top flag
+                self.h_done[lo:hi].copy_(self.d_done[lo:hi].view(torch.bool), non_blocking=True)
+                self.h_won[lo:hi].copy_(self.d_won[lo:hi].view(torch.bool), non_blocking=True)
         for st in self.streams:
             cur.wait_stream(st)
         cur.synchronize()
         b._mask_valid = True
         b.step_ctr += 1
-        fl = self.h_flags
-        return self.h_obs, self.h_reward, (fl & N.FLAG_DONE) != 0, (fl & N.FLAG_WON) != 0, {}
+        return self.h_obs, self.h_reward, self.h_done, self.h_won, {}
 
     def random_action(self) -> torch.Tensor:
         """board.random_action() with the result copied to pinned host memory (int32 [N])"""

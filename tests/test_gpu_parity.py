@@ -290,6 +290,38 @@ def test_match3env_dropin_contract(E):
     assert np.array_equal(obs2, d["init"][e])  # env.py:62: reset() without a seed keeps the seed
 
 
+def test_host_stepper_matches_device_api(E):
+    """HostStepper (host buffers in pinned memory, chunked over CUDA streams: the call bench.py's e2e times) returns
+    the same observations, rewards and done / won flags as BatchedMatch3Env.step on a twin environment, and both
+    match the oracle (Philox mode, ragged chunk sizes)."""
+    import torch
+    n, moves = 3000, 6  # not a multiple of the chunk count or of the 32-board tile
+    o = Oracle(9, 9, 6)
+    a_env = E.BatchedMatch3Env(n, seed=11, num_moves=moves, env_goal=60)
+    b_env = E.BatchedMatch3Env(n, seed=11, num_moves=moves, env_goal=60)
+    boards = np_(a_env.init()).astype(np.int64)
+    assert np.array_equal(boards, np_(b_env.init()))
+    hs = E.HostStepper(a_env, chunks=5)
+    score = np.zeros(n, dtype=np.int64)
+    for t in range(moves):
+        acts = hs.random_action()
+        assert acts.is_pinned() and acts.dtype == torch.int32
+        a = acts.numpy().copy()
+        obs, rew, done, won, _ = hs.step(acts)
+        for x in (obs, rew, done, won):
+            assert x.device.type == "cpu" and x.is_pinned()
+        assert done.dtype == torch.bool and won.dtype == torch.bool
+        obs2, rew2, done2, won2, _ = b_env.step(torch.from_numpy(a).to(b_env.board.device))
+        assert np.array_equal(obs.numpy(), np_(obs2)) and np.array_equal(rew.numpy(), np_(rew2))
+        assert np.array_equal(done.numpy(), np_(done2)) and np.array_equal(won.numpy(), np_(won2))
+        res = o.step_batch(boards, a, mode="philox", key=a_env.board.key, board0=0, step_ctr=t)
+        assert np.array_equal(obs.numpy(), res["boards"]) and np.array_equal(rew.numpy(), res["reward"])
+        score += res["reward"]
+        assert np.array_equal(won.numpy(), score >= 60)
+        assert np.array_equal(done.numpy(), (score >= 60) | (t == moves - 1))
+        boards = res["boards"]
+
+
 def test_boardv2_view_matches_golden_and_state_abc(E):
     d = load("episodes_6x6x4.npz")
     e = 2
