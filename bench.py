@@ -306,9 +306,14 @@ def run_ours(args):
                          "env_steps_finished_per_launch": finished, "handed_off_to_exact_kernel": handed_off,
                          "exact_kernel_avg_ms": avg_step_ms - avg_launch_ms, "step_avg_ms": avg_step_ms,
                          "peak_source": peak_src,
-                         "note": "instruction-issue bound, not HBM bound (DESIGN.md section 5): ~1600 integer "
-                                 "thread-instructions per env-step against 117 B; ncu: issue slots 58 % busy at 16 of "
-                                 "32 threads active, DRAM 12 %"},
+                         "integer_pipe": None if traffic is None else {
+                             "alu_pipe_pct_of_peak": traffic.get("alu_pipe_pct_of_peak"),
+                             "issue_slots_pct_busy": traffic.get("issue_slots_pct_busy"),
+                             "active_threads_per_instruction": traffic.get("active_threads_per_instruction"),
+                             "source": "ncu capture of this kernel, profiles/step_kernel_traffic.json"},
+                         "note": "integer-ALU-pipe bound, not HBM bound (DESIGN.md section 5): ~1700 integer "
+                                 "thread-instructions per env-step against 117 B; ncu: ALU pipe 84 % of peak, issue slots "
+                                 "62 % busy at 16.8 of 32 threads active, DRAM 14.5 %"},
             "cpu_baseline": cpu,
             "run": {"mean_cascades_per_step": mean_casc, "boards_without_legal_move": stuck, "boards_flagged": bad,
                     "episode_stats": stats},
