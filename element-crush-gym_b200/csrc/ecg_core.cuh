@@ -65,6 +65,32 @@ ECG_HD_NOINLINE PhiloxBlock philox_block(uint32_t c0, uint32_t c1, uint32_t c2, 
     return b;
 }
 
+// Sixteen refill tiles at once: the four base-n digits of each of the four words (most significant first), each
+// stored as (digit + 1) in a 4-bit field, first tile in the low nibble of lo.  Fields are never 0, so "lo == 0"
+// means "all used".  Out of line: only a refill of more than 12 tiles in one cascade iteration gets here.
+struct TileNibbles {
+    uint32_t lo, hi;
+};
+ECG_HD void pack_tiles(uint32_t x, uint32_t n, uint32_t &out, int shift) { // four digits of x -> out[shift .. shift+15]
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        out += (mulhi32(x, n) + 1u) << (shift + 4 * t);
+        x *= n;
+    }
+}
+template <int UNUSED = 0>
+ECG_HD_NOINLINE TileNibbles philox_block_tiles(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, uint32_t n) {
+    uint32_t w[4];
+    philox4x32_10(c0, c1, c2, c3, k0, k1, w);
+    TileNibbles t = {0u, 0u};
+    pack_tiles(w[0], n, t.lo, 0);
+    pack_tiles(w[1], n, t.lo, 16);
+    pack_tiles(w[2], n, t.hi, 0);
+    pack_tiles(w[3], n, t.hi, 16);
+    return t;
+}
+
 // Throughput mode: bounded ints by multiply-high of one u32 (no rejection).
 // Draw addressing inside the (board, step) substream (engine-defined; mirrored by the oracle's Philox mode):
 //   word 0: the random action pick of this step (philox_pick);
@@ -120,6 +146,31 @@ struct PhiloxRng {
         return j == 0 ? blk[0] : j == 1 ? blk[1] : j == 2 ? blk[2] : blk[3];
     }
     ECG_HD uint32_t below(uint32_t n) { return n <= 1u ? 0u : mulhi32(u32(), n); }
+    // The refill's view of the same digit stream (see digit() below): after seek(p) with p = 1 mod 4 and the block
+    // of p preset, first_tiles() packs the 12 tiles of words p, p+1, p+2 as nibbles (TileNibbles layout) and
+    // more_tiles() the 16 of every following block.  One multiply per tile on the FMA pipe, done by all lanes of
+    // the warp together, instead of digit bookkeeping inside the divergent per-hole loop.
+    ECG_HD void first_tiles(uint32_t n, uint32_t &lo, uint32_t &hi) {
+        if ((pos >> 2) != blk_idx) { // not preset by the caller
+            const PhiloxBlock nb = philox_block(pos >> 2, step, b0, b1, k0, k1);
+            blk[0] = nb.w[0];
+            blk[1] = nb.w[1];
+            blk[2] = nb.w[2];
+            blk[3] = nb.w[3];
+            blk_idx = pos >> 2;
+        }
+        lo = hi = 0u;
+        pack_tiles(blk[1], n, lo, 0);
+        pack_tiles(blk[2], n, lo, 16);
+        pack_tiles(blk[3], n, hi, 0);
+        pos = (pos | 3u) + 1u; // first word of the next block
+    }
+    ECG_HD void more_tiles(uint32_t n, uint32_t &lo, uint32_t &hi) {
+        const TileNibbles t = philox_block_tiles(pos >> 2, step, b0, b1, k0, k1, n);
+        lo = t.lo;
+        hi = t.hi;
+        pos += 4u;
+    }
     // Refill tiles: successive base-n digits of the fraction word / 2^32 (digit = hi32(x * n), x = lo32(x * n)),
     // 4 per word.  Each digit is uniform up to n^4 / 2^32 (3e-7 for 6 types).
     ECG_HD uint32_t digit(uint32_t n) {
@@ -1023,6 +1074,25 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
     const BB<G::W> holes = andn(G::valid(), b.p[0] | b.p[1] | b.p[2] | b.p[3]);
     if constexpr (RNG::ROW_MAJOR) {
         rng.seek((uint32_t)iter * 2048u + 1u);
+#if !defined(ECG_REFILL_DIGIT_LOOP)
+        uint32_t lo, hi; // the next tiles, one per nibble
+        rng.first_tiles(types, lo, hi);
+#pragma unroll
+        for (int w = 0; w < G::W; w++) {
+            uint32_t h = holes.w[w];
+            while (h) {
+                if (lo == 0u) rng.more_tiles(types, lo, hi);
+                const uint32_t bit = h & (0u - h);
+                h ^= bit;
+                deposit_bit<1>(b.p[0].w[w], lo, bit);
+                deposit_bit<2>(b.p[1].w[w], lo, bit);
+                deposit_bit<4>(b.p[2].w[w], lo, bit);
+                if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[w], lo, bit);
+                lo = funnel_r(lo, hi, 4);
+                hi >>= 4;
+            }
+        }
+#else
 #pragma unroll
         for (int w = 0; w < G::W; w++) {
             uint32_t h = holes.w[w];
@@ -1036,6 +1106,7 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
                 if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[w], v, bit);
             }
         }
+#endif
     } else {
         uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
         while (cols) {
