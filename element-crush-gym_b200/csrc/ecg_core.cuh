@@ -1080,16 +1080,19 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
 #pragma unroll
         for (int w = 0; w < G::W; w++) {
             uint32_t h = holes.w[w];
-            while (h) {
-                if (lo == 0u) rng.more_tiles(types, lo, hi);
-                const uint32_t bit = h & (0u - h);
-                h ^= bit;
-                deposit_bit<1>(b.p[0].w[w], lo, bit);
-                deposit_bit<2>(b.p[1].w[w], lo, bit);
-                deposit_bit<4>(b.p[2].w[w], lo, bit);
-                if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[w], lo, bit);
-                lo = funnel_r(lo, hi, 4);
-                hi >>= 4;
+            for (;;) {
+                while (h != 0u && lo != 0u) { // one compare-and-branch per tile; running out of tiles is rare
+                    const uint32_t bit = h & (0u - h);
+                    h ^= bit;
+                    deposit_bit<1>(b.p[0].w[w], lo, bit);
+                    deposit_bit<2>(b.p[1].w[w], lo, bit);
+                    deposit_bit<4>(b.p[2].w[w], lo, bit);
+                    if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[w], lo, bit);
+                    lo = funnel_r(lo, hi, 4);
+                    hi >>= 4;
+                }
+                if (h == 0u) break;
+                rng.more_tiles(types, lo, hi);
             }
         }
 #else
