@@ -312,8 +312,8 @@ def run_ours(args):
                              "active_threads_per_instruction": traffic.get("active_threads_per_instruction"),
                              "source": "ncu capture of this kernel, profiles/step_kernel_traffic.json"},
                          "note": "integer-ALU-pipe bound, not HBM bound (DESIGN.md section 5): ~1700 integer "
-                                 "thread-instructions per env-step against 117 B; ncu: ALU pipe 85.5 % of peak, issue slots "
-                                 "62 % busy at 17.3 of 32 threads active, DRAM 15 %"},
+                                 "thread-instructions per env-step against 117 B; ncu: ALU pipe 88 % of peak, issue slots "
+                                 "61 % busy at 18.2 of 32 threads active, DRAM 16 %"},
             "cpu_baseline": cpu,
             "run": {"mean_cascades_per_step": mean_casc, "boards_without_legal_move": stuck, "boards_flagged": bad,
                     "episode_stats": stats},
