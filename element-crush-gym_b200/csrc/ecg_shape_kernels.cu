@@ -414,8 +414,11 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
         if (io.n_jobs) n = *io.n_jobs;
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * lane_block(FAST) + threadIdx.x) >> 5);
-    // the job list of a two-kernel step is short (5 % of the boards): small chunks spread it over all warps
-    const int CHUNK = (!FAST && !ROLLOUT && io.n_jobs) ? 32 : ::CHUNK_BOARDS;
+    // The hand-off list of a two-kernel step is short (0.6 % of the boards: 94 k jobs for 2 368 warps): every warp takes
+    // ONE contiguous range of (almost) the same length.  Chunks of 32 handed round-robin left some warps with 64 jobs and
+    // others with 32 (6.98e9 env-steps/s at 9x9x6; chunks of 16: 7.11e9; equal ranges: 7.18e9).
+    const int nwarps_all = (int)((gridDim.x * lane_block(FAST)) >> 5);
+    const int CHUNK = (!FAST && !ROLLOUT && io.n_jobs) ? (n + nwarps_all - 1) / nwarps_all + (n == 0) : ::CHUNK_BOARDS;
     const int stride = (int)((gridDim.x * lane_block(FAST)) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
     int chunk0 = warp * CHUNK;
@@ -723,7 +726,7 @@ void launch_two_kernel_step(RefillDev rf, StepDev io, long long n, cudaStream_t 
 
 int op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
     const RolloutDev ro = {};
-    if (philox && io.handoff) {
+    if (philox && io.handoff && n <= (1ll << 29)) { // the job cursor's 32-bit arithmetic: 2 n + warps < 2^31
         if (wide) launch_two_kernel_step<SHW>(rf, io, n, s);
         else launch_two_kernel_step<SHN>(rf, io, n, s);
         return 2;
