@@ -31,7 +31,8 @@ class Refill(C.Structure):
     """struct ecg_refill"""
     _fields_ = [("mode", C.c_int32), ("stream_len", C.c_int32), ("stream", C.c_void_p),
                 ("stream_stride", C.c_int64), ("stream_pos", C.c_void_p), ("philox_key", C.c_uint64),
-                ("board0", C.c_uint64), ("step_ctr", C.c_uint32), ("reserved", C.c_uint32)]
+                ("board0", C.c_uint64), ("step_ctr", C.c_uint32), ("reserved", C.c_uint32),
+                ("stream_index", C.c_void_p)]
 
 
 class StepIO(C.Structure):
@@ -47,6 +48,7 @@ class StepIO(C.Structure):
 EXPORTS = {
     # name: (restype, argtypes)
     "ecg_version": (C.c_int, []),
+    "ecg_sizeof": (C.c_int, [C.c_int]),
     "ecg_last_error": (C.c_char_p, []),
     "ecg_launch_count": (C.c_int64, []),
     "ecg_config_init": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_int]),
@@ -83,6 +85,10 @@ def lib():
         for name, (res, args) in EXPORTS.items():
             fn = getattr(L, name)  # AttributeError = the library does not match include/ecg.h
             fn.restype, fn.argtypes = res, args
+        for which, st in enumerate((Config, Refill, StepIO)):  # ECG_SIZEOF_*: a stale stub must not reach ecg_step
+            if L.ecg_sizeof(which) != C.sizeof(st):
+                raise EcgError(f"{LIB_PATH}: sizeof({st.__name__}) is {L.ecg_sizeof(which)} in the library, "
+                               f"{C.sizeof(st)} in _native.py -- rebuild the library")
         _lib = L
     return _lib
 

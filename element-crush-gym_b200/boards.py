@@ -54,8 +54,10 @@ class BatchedBoards:
         self.key = int(key if key is not None else (cfg.seed if refill == "philox" else 0)) & (2 ** 64 - 1)
         self.stream = None
         self.stream_pos = None
+        self.stream_index = None  # replay: int32 [n], board i replays stream stream_index[i] (children of expand())
         self.stream_len = 0
         self.stream_stride = 0
+        self._moves_bound = max(int(n_actions), 0)  # host-side upper bound of moves_left (no device read needed)
         dev = self.device
         nb = self.L.ecg_boards_bytes(C.byref(self.nat), self.n) // 4
         nm = self.L.ecg_masks_bytes(C.byref(self.nat), self.n) // 4
@@ -111,6 +113,8 @@ class BatchedBoards:
             rf.stream_len = self.stream_len
             rf.stream_stride = self.stream_stride
             rf.stream_pos = self.stream_pos.data_ptr()
+            if self.stream_index is not None:
+                rf.stream_index = self.stream_index.data_ptr()
         return rf
 
     def set_arrays(self, arrays):
@@ -207,6 +211,7 @@ class BatchedBoards:
         N.check(self.L.ecg_step(C.byref(self.nat), C.byref(rf), C.byref(io), self.n, _stream(self.device)), "ecg_step")
         self._mask_valid = True
         self.step_ctr += 1
+        self._moves_bound = max(self._moves_bound - 1, 0)
         return self
 
     def rollout(self) -> torch.Tensor:
@@ -219,7 +224,8 @@ class BatchedBoards:
         N.check(self.L.ecg_rollout(C.byref(self.nat), C.byref(rf), _ptr(self.boards), _ptr(self.moves_left),
                                    _ptr(total), _ptr(steps), _ptr(self.status), self.n, _stream(self.device)),
                 "ecg_rollout")
-        self.step_ctr += int(self.moves_left.max().item()) if self.n else 0
+        self.step_ctr += self._moves_bound  # no board plays more moves than that: no device read, no sync
+        self._moves_bound = 0
         self.score += total.to(torch.int32)
         self.moves_left -= steps
         self._mask_valid = False
@@ -249,15 +255,18 @@ class BatchedBoards:
         c._mask_valid = self._mask_valid
         c.step_ctr = self.step_ctr
         c.stream, c.stream_len, c.stream_stride = self.stream, self.stream_len, self.stream_stride  # read-only, shared
+        c.stream_index = self.stream_index  # read-only, shared
         c.stream_pos = None if self.stream_pos is None else self.stream_pos.clone()
+        c._moves_bound = self._moves_bound
         return c
 
     def expand(self):
         """Every legal (board, action) pair stepped once, in ONE kernel (Node.expand for all children,
         mctslib/standard/mcts.py:31-42; the inner loop of greedy_action, boardv2.py:209-218).
         Returns (children: BatchedBoards with one board per pair, parent: int64 [P], action: int32 [P]);
-        pairs are ordered by (board, ascending action).  A child uses its parent's refill stream / Philox id,
-        like the reference where every child is stepped with np.random.seed(cfg.seed)."""
+        pairs are ordered by (board, ascending action).  A child is stepped with its parent's refill stream / Philox
+        id, like the reference where every child is stepped with np.random.seed(cfg.seed); in replay mode it keeps
+        replaying that stream afterwards (stream_index) from the position its step reached (stream_pos)."""
         legal = self.legal_mask() & (self.moves_left >= 1)[:, None]  # terminal boards have no children (boardv2.py:44)
         pairs = torch.nonzero(legal, as_tuple=False)  # sorted by (board, action)
         parent = pairs[:, 0].contiguous()
@@ -267,9 +276,14 @@ class BatchedBoards:
                               board0=self.board0, env_goal=self.env_goal, _empty=True)
         child.stream, child.stream_len, child.stream_stride = self.stream, self.stream_len, self.stream_stride
         child.step_ctr = self.step_ctr + 1
+        child._moves_bound = max(self._moves_bound - 1, 0)
+        src = parent.to(torch.int32).contiguous()
+        if self.refill_mode == "replay":
+            child.stream_pos = torch.zeros(p, dtype=torch.int32, device=self.device)
+            if self.stream_stride:  # per-board streams: child j replays the stream of its parent
+                child.stream_index = src if self.stream_index is None else self.stream_index[parent].contiguous()
         if p == 0:
             return child, parent, action
-        src = parent.to(torch.int32).contiguous()
         io = N.StepIO()
         io.boards_in = self.boards.data_ptr()
         io.boards_out = child.boards.data_ptr()
@@ -283,14 +297,13 @@ class BatchedBoards:
         io.env_goal = self.env_goal
         rf = self._refill()
         if self.refill_mode == "replay":
-            rf.stream_pos = None  # every child restarts the stream (np.random.seed at the top of apply_action)
+            # every child restarts the stream (np.random.seed at the top of apply_action); with explicit actions
+            # stream_pos is output only: the words the child's step consumed, where its next random pick continues
+            rf.stream_pos = child.stream_pos.data_ptr()
         N.check(self.L.ecg_step(C.byref(self.nat), C.byref(rf), C.byref(io), p, _stream(self.device)), "ecg_step")
         child.moves_left.copy_(self.moves_left[parent] - 1)
         child.score.copy_(self.score[parent] + child.step_reward)
         child._mask_valid = True
-        if self.refill_mode == "replay":  # a child continues on its parent's stream (strided per parent board)
-            child.stream_pos = torch.zeros(p, dtype=torch.int32, device=self.device)
-            child._stream_src = src
         return child, parent, action
 
     def greedy_action(self) -> torch.Tensor:

@@ -109,16 +109,24 @@ RefillDev to_dev(const ecg_refill *rf) {
     d.board0 = rf->board0;
     d.step_ctr = rf->step_ctr;
     d.stream_len = rf->stream_len;
+    d.stream_index = rf->stream_index;
     return d;
 }
 
 const ShapeOps *ops_for(int rows) {
     switch (rows) {
+    case 4: return shape_ops_4();
     case 5: return shape_ops_5();
     case 6: return shape_ops_6();
     case 7: return shape_ops_7();
+    case 8: return shape_ops_8();
     case 9: return shape_ops_9();
+    case 10: return shape_ops_10();
+    case 11: return shape_ops_11();
     case 12: return shape_ops_12();
+    case 13: return shape_ops_13();
+    case 14: return shape_ops_14();
+    case 15: return shape_ops_15();
     case 16: return shape_ops_16();
     default: return nullptr;
     }
@@ -147,14 +155,23 @@ int check_refill(const ecg_refill *rf) {
 extern "C" {
 
 int ecg_version(void) { return ECG_VERSION; }
+int ecg_sizeof(int which) {
+    switch (which) {
+    case ECG_SIZEOF_CONFIG: return (int)sizeof(ecg_config);
+    case ECG_SIZEOF_REFILL: return (int)sizeof(ecg_refill);
+    case ECG_SIZEOF_STEP_IO: return (int)sizeof(ecg_step_io);
+    default: return -1;
+    }
+}
 const char *ecg_last_error(void) { return g_err; }
 int64_t ecg_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int ecg_config_init(ecg_config *cfg, int rows, int cols, int types) {
     if (!cfg) return fail("cfg is NULL");
     if (rows != cols)
-        return fail("only square boards: the reference's action space rows*(cols-1)*2 (boardConfig.py:27) is wrong otherwise");
-    if (!ops_for(rows)) return fail("board size must be one of 5, 6, 7, 9, 12, 16");
+        return fail("only square boards: the reference's action space rows*(cols-1)*2 (boardConfig.py:27) is wrong otherwise "
+                    "and its own front end only builds (height, height) boards (main.py:168)");
+    if (!ops_for(rows)) return fail("board size must be in 4..16 (boardConfig.decode needs columns >= 4; 16 is the engine's limit)");
     if (types < 1 || types > 11) return fail("types must be in 1..11 (4-bit cell codes)");
     memset(cfg, 0, sizeof(*cfg));
     cfg->rows = rows;
@@ -256,7 +273,15 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
     if (io->flags && !(io->score && io->moves_left)) return fail("ecg_step: flags need score and moves_left");
     if (n <= 0) return 0;
     if (n > (1ll << 30)) return fail("ecg_step: at most 2^30 boards per call");
-    if (io->src_index && io->boards_out == io->boards_in) return fail("ecg_step: src_index needs boards_out != boards_in");
+    if (io->src_index) {
+        // job i reads board src_index[i] and writes every output at i: an in/out array would be read at one index
+        // while another job writes it
+        if (io->boards_out == io->boards_in) return fail("ecg_step: src_index needs boards_out != boards_in");
+        if (io->moves_left || io->score)
+            return fail("ecg_step: src_index cannot be combined with the in/out arrays moves_left / score");
+        if (rf->mode == ECG_REFILL_REPLAY && rf->stream_pos && !io->actions)
+            return fail("ecg_step: src_index with random picks (actions == NULL) cannot take an in/out stream_pos");
+    }
     StepDev sd;
     sd.boards_in = io->boards_in;
     sd.boards_out = io->boards_out;

@@ -13,6 +13,7 @@ struct RefillDev {
     unsigned long long key, board0;
     uint32_t step_ctr;
     int stream_len;
+    const int32_t *stream_index; // replay, optional: board i replays stream stream_index[i]
 };
 
 struct StepDev {
@@ -56,11 +57,18 @@ struct ShapeOps {
                     cudaStream_t s);
 };
 
+const ShapeOps *shape_ops_4();
 const ShapeOps *shape_ops_5();
 const ShapeOps *shape_ops_6();
 const ShapeOps *shape_ops_7();
+const ShapeOps *shape_ops_8();
 const ShapeOps *shape_ops_9();
+const ShapeOps *shape_ops_10();
+const ShapeOps *shape_ops_11();
 const ShapeOps *shape_ops_12();
+const ShapeOps *shape_ops_13();
+const ShapeOps *shape_ops_14();
+const ShapeOps *shape_ops_15();
 const ShapeOps *shape_ops_16();
 
 } // namespace ecg

@@ -99,6 +99,11 @@ __device__ __forceinline__ void store_mask(uint32_t *mask, long long i, const BB
     for (int k = 0; k < G::W; k++) ECG_ST(base + (G::W + k) * 32, VL.w[k]);
 }
 
+// replay: the raw MT19937 words of board i (ecg_refill.stream_index redirects boards to shared streams)
+__device__ __forceinline__ const uint32_t *stream_of(const RefillDev &rf, long long i) {
+    return rf.stream + (rf.stream_index ? (long long)rf.stream_index[i] : i) * rf.stream_stride;
+}
+
 template <class SH>
 __device__ __forceinline__ void legal_of(const Board<typename SH::G> &b, BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
     using G = typename SH::G;
@@ -175,7 +180,14 @@ __global__ void __launch_bounds__(BLOCK) unpack_kernel(const void *boards, T *__
             if (VEC == 1) dst[e] = (T)value;
             else packed |= (uint32_t)value << (8 * v);
         }
-        if (VEC == 4) *reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(dst) + e0) = packed;
+        if (VEC == 4) {
+            uint8_t *d8 = reinterpret_cast<uint8_t *>(dst) + e0;
+            if (e0 + VEC <= total) {
+                *reinterpret_cast<uint32_t *>(d8) = packed;
+            } else { // the last word of a partial tile: only the cells that exist (total need not be a multiple of 4)
+                for (int v = 0; e0 + v < total; v++) d8[v] = (uint8_t)(packed >> (8 * v));
+            }
+        }
     }
 }
 
@@ -206,8 +218,6 @@ __global__ void __launch_bounds__(BLOCK) unpack_mask_kernel(const uint32_t *mask
     const bool vertical = k >= G::C - 1;
     const int bit = r * G::S + (vertical ? k - (G::C - 1) : k);
     const uint32_t w = mask[(i >> 5) * (2 * G::W * 32) + ((vertical ? G::W : 0) + (bit >> 5)) * 32 + (i & 31)];
-    const int a_unused = 0;
-    (void)a_unused;
     out[t] = (w >> (bit & 31)) & 1u;
 }
 
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(BLOCK) random_action_kernel(RefillDev rf, cons
         a = swaps_select<G>(HL, VL, (int)philox_pick(rf.key, rf.board0 + (unsigned long long)i, rf.step_ctr, (uint32_t)cnt));
     } else { // np.random.choice(legal_actions): k-th legal action in ascending action order
         ReplayRng rng;
-        rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
+        rng.init(stream_of(rf, i), (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
         uint32_t m[G::AW];
         swaps_to_actions<G>(HL, VL, m);
         a = mask_select<G>(m, (int)rng.below((uint32_t)cnt));
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards,
     Board<G> b;
     typename RngOf<PHILOX>::type rng;
     if constexpr (PHILOX) rng.init(rf.key, rf.board0 + (unsigned long long)i, 0xFFFFFFFFu);
-    else rng.init(rf.stream + i * rf.stream_stride, (uint32_t)rf.stream_len, 0u);
+    else rng.init(stream_of(rf, i), (uint32_t)rf.stream_len, 0u);
     init_board<SH>(b, (uint32_t)types, rng);
     store_board<G>(boards, i, b);
     if (status) status[i] = rng.overflow ? (uint8_t)ST_STREAM_OVERFLOW : (uint8_t)0;
@@ -491,7 +501,8 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                 if (io.src_index) src = io.src_index[idx];
             step = rf.step_ctr;
             rpos = 0;
-            if constexpr (!PHILOX) rpos = rf.stream_pos ? rf.stream_pos[src] : 0u;
+            if constexpr (!PHILOX) // expanding (board, action) pairs: stream_pos is output only, indexed by job
+                rpos = (rf.stream_pos && (ROLLOUT || !(io.actions && io.src_index))) ? rf.stream_pos[src] : 0u;
             if constexpr (ROLLOUT) {
                 load_board<G>(ro.boards, idx, L.bd);
                 moves = ro.moves_left[idx];
@@ -549,7 +560,7 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                     action = action_of_swap<G>(b1, vertical);
                 } else { // np.random.choice(legal_actions): ascending action order, numpy's masked rejection
                     ReplayRng rng;
-                    rng.init(rf.stream + (long long)src * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+                    rng.init(stream_of(rf, src), (uint32_t)rf.stream_len, rpos);
                     uint32_t m[G::AW];
                     swaps_to_actions<G>(HL, VL, m);
                     action = mask_select<G>(m, (int)rng.below((uint32_t)c));
@@ -597,7 +608,7 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                 rng.init(rf.key, rf.board0 + (unsigned long long)src, step);
                 rng.preset_block(blk_index, blk);
             } else {
-                rng.init(rf.stream + (long long)src * rf.stream_stride, (uint32_t)rf.stream_len, rpos);
+                rng.init(stream_of(rf, src), (uint32_t)rf.stream_len, rpos);
             }
             const bool fin = step_iter<SH, typename RngOf<PHILOX>::type, FAST>(L, rng, (uint32_t)types, HL, VL, handoff);
             if constexpr (!PHILOX) rpos = rng.pos;

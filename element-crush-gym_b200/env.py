@@ -147,7 +147,10 @@ class HostStepper:
         rf = b._refill()
         rf.board0 = b.board0 + lo
         if b.refill_mode == "replay":
-            rf.stream = b.stream.data_ptr() + 4 * lo * b.stream_stride
+            if b.stream_index is not None:
+                rf.stream_index = b.stream_index[lo:].data_ptr()
+            else:
+                rf.stream = b.stream.data_ptr() + 4 * lo * b.stream_stride
             rf.stream_pos = b.stream_pos[lo:].data_ptr()
         return io, rf
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ECG_VERSION 102
+#define ECG_VERSION 103
 
 /* per-board status bits */
 #define ECG_ST_TERMINAL 1        /* n_actions < 1: board returned unchanged (boardv2.py:44-45) */
@@ -69,6 +69,9 @@ typedef struct ecg_refill {
     uint64_t board0;         /* philox: global index of board 0 of this call (shard offset) */
     uint32_t step_ctr;       /* philox: step counter of this call (a rollout uses step_ctr + t) */
     uint32_t reserved;
+    const int32_t *stream_index; /* replay, optional [n]: board i replays the stream at stream + stream_index[i] *
+                                    stream_stride instead of i * stream_stride (children of an expansion keep their
+                                    parent's stream, boardv2.py:46: every BoardV2 reseeds with the same cfg.seed) */
 } ecg_refill;
 
 /* Buffers of one lockstep step.  n-element arrays are plain board-indexed; boards/masks are packed. */
@@ -90,7 +93,10 @@ typedef struct ecg_step_io {
     const int32_t *src_index; /* optional [n]: job i steps board src_index[i] of boards_in (and uses that board's
                                  refill stream / Philox id, moves_left, score, mask_in) and writes every output at i:
                                  "expand these (board, action) pairs" = Node.expand / greedy_action (boardv2.py:209-218,
-                                 mctslib/standard/mcts.py:31-42).  Needs boards_out != boards_in. */
+                                 mctslib/standard/mcts.py:31-42).  Needs boards_out != boards_in, and moves_left ==
+                                 score == NULL (in/out arrays would be read at src_index[i] while job src_index[i]
+                                 writes them); replay mode with actions == NULL also needs stream_pos == NULL.  With
+                                 explicit actions stream_pos is output only: [i] = words this step consumed. */
     int32_t *scratch;        /* optional work list, [n + 1] int32, contents irrelevant on entry and exit.  Philox mode
                                 only: when given, the step runs as TWO kernels -- the common-case kernel over all n
                                 boards, which hands the boards that need a rare path (intersecting runs, runs of 6+,
@@ -99,12 +105,18 @@ typedef struct ecg_step_io {
 } ecg_step_io;
 
 int ecg_version(void);
+/* sizeof the library's own structs, for binders to check their stubs against (a short ecg_step_io would make
+ * ecg_step read past the caller's struct): which = ECG_SIZEOF_* */
+#define ECG_SIZEOF_CONFIG 0
+#define ECG_SIZEOF_REFILL 1
+#define ECG_SIZEOF_STEP_IO 2
+int ecg_sizeof(int which);
 const char *ecg_last_error(void);
 /* kernels launched by this process so far (bench.py's gpu_launches) */
 int64_t ecg_launch_count(void);
 
 /* BoardConfig.__post_init__ (boardConfig.py:26-43).  rows == cols in 4..16, types in 1..11;
- * shapes built into the library: 5, 6, 7, 9, 12, 16. */
+ * every size 4..16 is built into the library (one kernel object per size). */
 int ecg_config_init(ecg_config *cfg, int rows, int cols, int types);
 /* bytes of a packed board / mask buffer for n boards (n is rounded up to a whole tile) */
 int64_t ecg_boards_bytes(const ecg_config *cfg, int64_t n);

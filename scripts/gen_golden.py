@@ -26,6 +26,8 @@ from match3tile.boardFunctions import get_match_spawn_mask, get_matches, legal_a
 from match3tile.boardv2 import BoardV2  # noqa: E402
 
 SHAPES = [(9, 9, 6), (6, 6, 4), (12, 12, 7), (16, 16, 8), (6, 6, 3), (5, 5, 2)]
+# round 2: the other square sizes boardConfig accepts (main.py:168 only builds (height, height) boards); smaller files
+EXTRA_SHAPES = [(4, 4, 4), (7, 7, 5), (8, 8, 5), (10, 10, 6), (11, 11, 7), (13, 13, 9), (14, 14, 6), (15, 15, 8)]
 
 
 class Timeout(Exception):
@@ -77,23 +79,33 @@ def apply(cfg, arr, action, timeout=2):
 def gen_episodes(shape, seeds, moves=20):
     R, Cc, T = shape
     init, actions, boards, rewards, casc, legal = [], [], [], [], [], []
+    kept = []
     for s in seeds:
         cfg = BoardConfig(seed=int(s), rows=R, columns=Cc, types=T)
-        state = BoardV2(moves, cfg)
-        init.append(state.array.copy())
-        np.random.seed(cfg.seed)
-        ea, eb, er, ec, el = [], [], [], [], []
-        while not state.is_terminal:
-            la = list(state.legal_actions)
-            m = np.zeros(cfg.action_space, dtype=np.uint8)
-            m[la] = 1
-            a = np.random.choice(la)
-            prev = state.reward
-            with Recorder() as rec:
-                state = state.apply_action(a)
-            ea.append(int(a)); eb.append(state.array.copy()); er.append(int(state.reward - prev))
-            ec.append(rec.clips); el.append(m)
+        signal.signal(signal.SIGALRM, _alarm)
+        signal.alarm(20)  # tiny boards can spin in the reference's shuffle loop (boardv2.py:188-194): skip that seed
+        try:
+            state = BoardV2(moves, cfg)
+            i0 = state.array.copy()
+            np.random.seed(cfg.seed)
+            ea, eb, er, ec, el = [], [], [], [], []
+            while not state.is_terminal:
+                la = list(state.legal_actions)
+                m = np.zeros(cfg.action_space, dtype=np.uint8)
+                m[la] = 1
+                a = np.random.choice(la)
+                prev = state.reward
+                with Recorder() as rec:
+                    state = state.apply_action(a)
+                ea.append(int(a)); eb.append(state.array.copy()); er.append(int(state.reward - prev))
+                ec.append(rec.clips); el.append(m)
+        except (Timeout, ValueError):  # ValueError: np.random.choice on an empty legal set
+            continue
+        finally:
+            signal.alarm(0)
+        kept.append(s); init.append(i0)
         actions.append(ea); boards.append(eb); rewards.append(er); casc.append(ec); legal.append(el)
+    seeds = kept
     return dict(seeds=np.array(seeds, dtype=np.uint32), init=np.array(init, dtype=np.int8),
                 actions=np.array(actions, dtype=np.int16), boards=np.array(boards, dtype=np.int8),
                 rewards=np.array(rewards, dtype=np.int32), cascades=np.array(casc, dtype=np.int16),
@@ -139,7 +151,14 @@ def gen_steps(shape, n_random, n_special, seed0):
             la = state.legal_actions
             a = int(rng.integers(cfg.action_space)) if (rng.integers(4) == 0 or not la) else int(la[rng.integers(len(la))])
             record(cfg, state.array, a)
-            state = state.apply_action(a)
+            signal.signal(signal.SIGALRM, _alarm)
+            signal.alarm(5)  # small boards can spin in the reference's shuffle loop: drop the episode
+            try:
+                state = state.apply_action(a)
+            except Timeout:
+                break
+            finally:
+                signal.alarm(0)
     # (b) planted specials (all pair branches boardv2.py:81-136 + trigger pass :141-154)
     k = 0
     while k < n_special:
@@ -249,11 +268,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--extra-only", action="store_true", help="only the round-2 EXTRA_SHAPES fixtures")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     sc = args.scale
-    np.savez_compressed(os.path.join(args.out, "rng.npz"), **gen_rng())
-    print("rng done", flush=True)
+    if not args.extra_only:
+        np.savez_compressed(os.path.join(args.out, "rng.npz"), **gen_rng())
+        print("rng done", flush=True)
+    for shape in EXTRA_SHAPES:
+        tag = "%dx%dx%d" % shape
+        np.savez_compressed(os.path.join(args.out, f"episodes_{tag}.npz"), **gen_episodes(shape, list(range(1, int(6 * sc) + 1))))
+        seed0 = shape[0] * 10000 + shape[1] * 100 + shape[2]
+        np.savez_compressed(os.path.join(args.out, f"steps_{tag}.npz"), **gen_steps(shape, int(100 * sc), int(80 * sc), seed0=seed0))
+        np.savez_compressed(os.path.join(args.out, f"funcs_{tag}.npz"), **gen_funcs(shape, int(80 * sc), seed0=seed0 + 1))
+        print(tag, "done", flush=True)
+    if args.extra_only:
+        return
     for shape in SHAPES:
         tag = "%dx%dx%d" % shape
         main_shape = shape == (9, 9, 6)

@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 SHAPES = [(9, 9, 6), (6, 6, 4), (12, 12, 7), (16, 16, 8), (6, 6, 3), (5, 5, 2)]
+# round 2: every other square size boardConfig accepts, with smaller reference-generated fixtures
+EXTRA_SHAPES = [(4, 4, 4), (7, 7, 5), (8, 8, 5), (10, 10, 6), (11, 11, 7), (13, 13, 9), (14, 14, 6), (15, 15, 8)]
+ALL_SHAPES = SHAPES + EXTRA_SHAPES
 
 
 def pytest_configure(config):

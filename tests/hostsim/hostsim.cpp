@@ -160,18 +160,22 @@ static void init_t(int types, const uint32_t *raw, int64_t raw_stride, int64_t r
     }
 }
 
-#define DISPATCH(rows, types, CALL)                                                      \
-    do {                                                                                 \
-        const bool wide = (types) >= 8;                                                  \
-        switch (rows) {                                                                  \
-        case 5: if (wide) { using SH = Shape<5, 5, 4, true>; CALL; } else { using SH = Shape<5, 5, 3, false>; CALL; } return 0;     \
-        case 6: if (wide) { using SH = Shape<6, 6, 4, true>; CALL; } else { using SH = Shape<6, 6, 3, false>; CALL; } return 0;     \
-        case 7: if (wide) { using SH = Shape<7, 7, 4, true>; CALL; } else { using SH = Shape<7, 7, 3, false>; CALL; } return 0;     \
-        case 9: if (wide) { using SH = Shape<9, 9, 4, true>; CALL; } else { using SH = Shape<9, 9, 3, false>; CALL; } return 0;     \
-        case 12: if (wide) { using SH = Shape<12, 12, 4, true>; CALL; } else { using SH = Shape<12, 12, 3, false>; CALL; } return 0; \
-        case 16: if (wide) { using SH = Shape<16, 16, 4, true>; CALL; } else { using SH = Shape<16, 16, 3, false>; CALL; } return 0; \
-        default: return -1;                                                              \
-        }                                                                                \
+// One library per board size (-DHS_SIZE=N, tests/hostsim/hostsim.py builds them in parallel): the core is a large
+// header and thirteen sizes x two type widths in one translation unit took g++ nine minutes.
+#ifndef HS_SIZE
+#error "compile with -DHS_SIZE=<board size>"
+#endif
+#define DISPATCH(rows, types, CALL)                              \
+    do {                                                         \
+        if ((rows) != HS_SIZE) return -1;                        \
+        if ((types) >= 8) {                                      \
+            using SH = Shape<HS_SIZE, HS_SIZE, 4, true>;         \
+            CALL;                                                \
+        } else {                                                 \
+            using SH = Shape<HS_SIZE, HS_SIZE, 3, false>;        \
+            CALL;                                                \
+        }                                                        \
+        return 0;                                                \
     } while (0)
 
 static int64_t g_handoffs = 0;

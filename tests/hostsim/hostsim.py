@@ -6,28 +6,47 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libecg_hostsim.so")
 _CSRC = os.path.join(_HERE, "..", "..", "element-crush-gym_b200", "csrc")
+SIZES = tuple(range(4, 17))
 
 
-def build(force=False):
+def _lib_path(size):
+    return os.path.join(_HERE, f"libecg_hostsim_{size}.so")
+
+
+def _stale(size):
+    lib = _lib_path(size)
     srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_CSRC, "ecg_core.cuh"), os.path.join(_CSRC, "ecg_bits.cuh")]
-    stale = not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
-    if force or stale:
-        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB,
-                        os.path.join(_HERE, "hostsim.cpp")], check=True)
-    return _LIB
+    return not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs)
 
 
-_lib = None
+def _compile(size):
+    tmp = _lib_path(size) + f".{os.getpid()}.tmp"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-unknown-pragmas", f"-DHS_SIZE={size}",
+                    "-o", tmp, os.path.join(_HERE, "hostsim.cpp")], check=True)
+    os.replace(tmp, _lib_path(size))
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB)
-    return _lib
+def build(sizes=SIZES, force=False):
+    """one library per board size, the stale ones compiled in parallel"""
+    todo = [n for n in sizes if force or _stale(n)]
+    if todo:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            list(ex.map(_compile, todo))
+    return [_lib_path(n) for n in sizes]
+
+
+_libs = {}
+
+
+def lib(size):
+    if size not in _libs:
+        build((size,))
+        L = C.CDLL(_lib_path(size))
+        L.hs_handoffs.restype = C.c_int64
+        _libs[size] = L
+    return _libs[size]
 
 
 def _p(a):
@@ -38,7 +57,7 @@ class HostSim:
     def __init__(self, rows, cols, types):
         self.rows, self.cols, self.types = rows, cols, types
         self.A = rows * (cols - 1) * 2
-        self.L = lib()
+        self.L = lib(rows)
 
     def step(self, boards, actions, *, mode, raw=None, key=0, board0=0, step_ctr=0, moves_left=None, two_pass=False):
         """two_pass: the two-kernel step on the host -- common-case build first, exact build on a hand-off"""
@@ -60,7 +79,6 @@ class HostSim:
                             C.c_uint64(key), C.c_uint64(board0), C.c_uint32(step_ctr), _p(boards), _p(actions), _p(ml),
                             _p(out), _p(reward), _p(casc), _p(status), _p(legal), C.c_int64(n))
         assert rc == 0
-        self.L.hs_handoffs.restype = C.c_int64
         return {"boards": out, "reward": reward, "cascades": casc, "status": status, "legal": legal.astype(bool),
                 "handoffs": int(self.L.hs_handoffs())}
 

@@ -25,14 +25,37 @@ def test_library_exports_every_declared_symbol(E):
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(E._native.EXPORTS), declared ^ set(E._native.EXPORTS)
-    assert E._native.lib().ecg_version() == 102
+    assert E._native.lib().ecg_version() == 103
 
 
 def test_struct_layouts_match_header(E):
     N = E._native
     assert C.sizeof(N.Config) == 14 * 4
-    assert C.sizeof(N.Refill) == 56 and N.Refill.stream.offset == 8 and N.Refill.philox_key.offset == 32
+    assert C.sizeof(N.Refill) == 64 and N.Refill.stream.offset == 8 and N.Refill.philox_key.offset == 32
+    assert N.Refill.stream_index.offset == 56
     assert C.sizeof(N.StepIO) == 12 * 8 + 8 + 8 + 8 and N.StepIO.env_goal.offset == 96 and N.StepIO.src_index.offset == 104
+    L = N.lib()
+    for which, st in enumerate((N.Config, N.Refill, N.StepIO)):  # ECG_SIZEOF_CONFIG / _REFILL / _STEP_IO
+        assert L.ecg_sizeof(which) == C.sizeof(st)
+    assert L.ecg_sizeof(3) == -1
+
+
+def test_integration_md_stubs_match_the_library(E):
+    """The ctypes stubs INTEGRATION.md tells a maintainer to copy must be the structs the library reads: a short
+    ecg_step_io makes ecg_step read past the caller's struct (round-1 finding: 104 B documented, 120 B read)."""
+    import re
+    N = E._native
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "class EcgStepIO" in b)
+    stubs_src = block.split("\nL = C.CDLL")[0]  # the import line and the three class statements
+    ns = {}
+    exec(compile(stubs_src.replace(", torch", ""), "INTEGRATION.md", "exec"), ns)
+    L = N.lib()
+    for which, (name, mine) in enumerate((("EcgConfig", N.Config), ("EcgRefill", N.Refill), ("EcgStepIO", N.StepIO))):
+        stub = ns[name]
+        assert C.sizeof(stub) == C.sizeof(mine) == L.ecg_sizeof(which), name
+        assert [(f[0], getattr(stub, f[0]).offset, getattr(stub, f[0]).size) for f in stub._fields_] == \
+               [(f[0], getattr(mine, f[0]).offset, getattr(mine, f[0]).size) for f in mine._fields_], name
 
 
 def test_config_matches_reference_constants(E):
@@ -65,7 +88,9 @@ def test_argument_errors_are_reported_not_raised_in_c(E):
     L = N.lib()
     cfg = N.Config()
     assert L.ecg_config_init(C.byref(cfg), 9, 8, 6) < 0 and b"square" in L.ecg_last_error()
-    assert L.ecg_config_init(C.byref(cfg), 10, 10, 6) < 0
+    assert L.ecg_config_init(C.byref(cfg), 3, 3, 6) < 0 and L.ecg_config_init(C.byref(cfg), 17, 17, 6) < 0
+    for size in range(4, 17):  # every square size the reference can run is built in
+        assert L.ecg_config_init(C.byref(cfg), size, size, 6) == 0 and cfg.action_space == size * (size - 1) * 2
     assert L.ecg_config_init(C.byref(cfg), 9, 9, 12) < 0
     with pytest.raises(E.EcgError):
         E.BoardConfig(seed=1, rows=9, columns=9, types=0)
@@ -76,6 +101,13 @@ def test_argument_errors_are_reported_not_raised_in_c(E):
     assert L.ecg_step(C.byref(cfg), C.byref(rf), C.byref(io), 10, None) < 0
     rf.mode = N.REFILL_PHILOX
     assert L.ecg_step(C.byref(cfg), C.byref(rf), C.byref(io), 10, None) < 0 and b"boards_in" in L.ecg_last_error()
+    # expanding (board, action) pairs: in/out arrays would race between jobs (read at src_index[i], written at i)
+    io.boards_in, io.boards_out, io.actions, io.src_index = 256, 512, 768, 1024  # never dereferenced: checks come first
+    io.moves_left = 2048
+    assert L.ecg_step(C.byref(cfg), C.byref(rf), C.byref(io), 10, None) < 0 and b"src_index" in L.ecg_last_error()
+    io.moves_left = None
+    io.boards_out = io.boards_in
+    assert L.ecg_step(C.byref(cfg), C.byref(rf), C.byref(io), 10, None) < 0 and b"src_index" in L.ecg_last_error()
     cfg.board_words = 13  # a config not made by ecg_config_init
     assert L.ecg_legal_mask(C.byref(cfg), None, None, 1, None) < 0
     assert L.ecg_boards_bytes(C.byref(E.BoardConfig(seed=1).native), 33) == 64 * 48

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from conftest import GOLDEN, SHAPES  # noqa: E402
+from conftest import ALL_SHAPES, GOLDEN, SHAPES  # noqa: E402
 from oracle.oracle import Oracle, ST_CASCADE_CAP, ST_SHUFFLE_CAP, ST_STREAM_OVERFLOW  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -36,7 +36,7 @@ def np_(t):
     return t.cpu().numpy()
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_pack_unpack_roundtrip_and_bad_cells(E, shape):
     import torch
     o = Oracle(*shape)
@@ -55,7 +55,7 @@ def test_pack_unpack_roundtrip_and_bad_cells(E, shape):
         E.BatchedBoards(cfg_of(E, shape), n, arrays=bad, key=KEY)
 
 
-@pytest.mark.parametrize("shape", SHAPES[:5])
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_legal_mask_golden(E, shape):
     d = load("funcs_%dx%dx%d.npz" % shape)
     o = Oracle(*shape)
@@ -66,7 +66,7 @@ def test_legal_mask_golden(E, shape):
     assert bb.legal_actions[3] == np.flatnonzero(legal[3]).tolist()
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_golden_single_steps_replay(E, shape):
     d = load("steps_%dx%dx%d.npz" % shape)
     n = len(d["actions"])
@@ -93,7 +93,7 @@ def test_golden_shuffle_cases(E):
         assert int(bb.step_reward[0]) == d["rewards"][i] and int(bb.cascades[0]) == d["cascades"][i]
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_golden_episodes_random_task(E, shape):
     """samplerTasks.random_task (:9-14) replayed on the GPU: init boards from the MT19937 stream, picks by
     numpy's masked rejection on the same stream, 20 steps; then the same episodes in ONE rollout kernel."""

@@ -9,18 +9,24 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from conftest import GOLDEN, SHAPES  # noqa: E402
+from conftest import ALL_SHAPES, GOLDEN, SHAPES  # noqa: E402
+from hostsim import hostsim as _hostsim  # noqa: E402
 from hostsim.hostsim import HostSim  # noqa: E402
 from oracle.oracle import Oracle, ST_CASCADE_CAP, ST_SHUFFLE_CAP, ST_STREAM_OVERFLOW, ST_TERMINAL, ST_BAD_ACTION  # noqa: E402
 
 KEY = 0x1234567890ABCDEF
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _host_builds():
+    _hostsim.build()  # one library per board size; a fresh checkout compiles them in parallel (about a minute)
+
+
 def load(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_golden_single_steps_replay(shape):
     d = load("steps_%dx%dx%d.npz" % shape)
     h = HostSim(*shape)
@@ -32,7 +38,7 @@ def test_golden_single_steps_replay(shape):
     assert np.array_equal(res["cascades"], d["cascades"])
 
 
-@pytest.mark.parametrize("shape", SHAPES[:5])
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_golden_functions(shape):
     d = load("funcs_%dx%dx%d.npz" % shape)
     o, h = Oracle(*shape), HostSim(*shape)
@@ -61,7 +67,7 @@ def test_golden_shuffle_cases():
         assert res["reward"][0] == d["rewards"][i] and res["cascades"][0] == d["cascades"][i]
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_golden_episodes_replay(shape):
     """Whole random_task episodes (init board from the MT stream, masked-rejection picks, steps)."""
     d = load("episodes_%dx%dx%d.npz" % shape)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, SHAPES
+from conftest import ALL_SHAPES, GOLDEN, SHAPES
 from oracle.oracle import Oracle, ST_SHUFFLE_CAP
 
 
@@ -47,7 +47,7 @@ def test_rng_row_shuffle_matches_numpy():
         assert np.array_equal(out[:, 0] - 1, d["shuffle9"][i])
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_episodes(shape):
     """random_task trajectories: init board, every chosen action, board, reward, cascade count, legal set."""
     d = load("episodes_%dx%dx%d.npz" % shape)
@@ -75,7 +75,7 @@ def test_episodes(shape):
         assert np.array_equal(fb, d["boards"][e, -1])
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_single_steps(shape):
     d = load("steps_%dx%dx%d.npz" % shape)
     o = Oracle(*shape)
@@ -94,7 +94,7 @@ def test_single_steps(shape):
     assert np.array_equal(res["cascades"], d["cascades"])
 
 
-@pytest.mark.parametrize("shape", SHAPES[:5])
+@pytest.mark.parametrize("shape", ALL_SHAPES)
 def test_functions(shape):
     d = load("funcs_%dx%dx%d.npz" % shape)
     o = Oracle(*shape)
