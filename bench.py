@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- 9x9x6 env-steps/sec (cascades included) of the batched stepping engine.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--scaling weak|strong] [--impl reference]
 
-Workload = BASELINE.json configs[2] (SURVEY.md 8d "config 3"): 2^24 lockstep 9x9x6 boards PER GPU (weak
-scaling; Philox keyed by global board index, so results do not depend on N), each step = pick a uniformly
-random legal action from the previous legal mask -> swap -> full cascade -> reward/done/won -> new legal mask.
-One step of all boards is ONE launch of the step kernel.  Inputs are resident in HBM (1.1 GB of boards + masks,
-far larger than the 126 MB L2, so no explicit L2 flush is needed between steps).
+Workload = BASELINE.json configs[2] (SURVEY.md 8d "config 3"): lockstep 9x9x6 boards, Philox keyed by global board
+index (results do not depend on N), each step = pick a uniformly random legal action from the previous legal mask ->
+swap -> full cascade -> reward/done/won -> new legal mask.  One step of all boards is ONE ecg_step call (two kernel
+launches).  Inputs are resident in HBM (1.1 GB of boards + masks per 2^24 boards, far larger than the 126 MB L2, so
+no explicit L2 flush is needed between steps).
+
+--scaling weak (default): 2^24 boards PER GPU, `value` is that run; the JSON line also carries "strong" = the same
+K steps on 2^24 boards IN TOTAL split evenly over the N GPUs (BASELINE configs[2] "16M boards ... sharded over
+1/2/4/8").  --scaling strong swaps the two.
 
 The JSON line also carries
-  e2e          the same metric through the public host-buffer API (HostStepper): per step the actions are
-               fetched to pinned host memory (board.random_action()), copied back H2D, and obs/reward/flags are
-               read D2H, all inside the timed region;
+  sustained    >= 5 s of back-to-back steps with SM clock and power sampled over them (the K-step region is 0.05 s);
+  replay       the REFERENCE's dynamics at the same size: ECG_REFILL_REPLAY, every step restarts the MT19937 stream
+               of cfg.seed (boardv2.py:46) -- one stream shared by all boards, and 4096 distinct streams;
+  e2e          the same metric through the public host-buffer API (HostStepper): per step the actions are fetched to
+               pinned host memory (board.random_action()), copied back H2D, and obs/reward/done/won are read D2H, all
+               inside the timed region; "e2e" is the env-contract form (uint8 cells), "e2e_nibbles" the 4-bit form;
   roofline     algorithmic bytes per launch (117 B per env-step) / average step-kernel duration;
   cpu_baseline the CPU oracle port (oracle/, test infrastructure) timed on this box's host cores, rank 0, N=1.
 --impl reference times that CPU port on all host threads as the reference arm (the reference itself is pure
@@ -47,14 +54,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU")
+    ap.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (weak) / in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--sustained-seconds", type=float, default=5.0)
+    ap.add_argument("--replay-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the strong/weak twin, sustained and replay legs")
     return ap.parse_args()
 
 
 def workload(boards_per_gpu, n_gpus):
+    boards_per_gpu = int(boards_per_gpu)
     return {
         "workload": "configs[2]: lockstep 9x9x6 boards, random legal action from the previous mask + step + "
                     "cascade + reward/done/won + legal-swap mask every step, Philox4x32-10 refill",
@@ -107,7 +119,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -115,6 +127,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -123,7 +136,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
-        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_min": min(sm), "power_w_median": statistics.median(sorted(pw)[len(pw) // 2:]) if pw else None}
 
 
 # ------------------------------------------------------------------ CPU port (oracle) legs
@@ -206,8 +220,10 @@ def run_ours(args):
     import torch.distributed as tdist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    n = args.boards
     L = E._native.lib()
+    strong_main = args.scaling == "strong"
+    first, count = E.dist.shard_range(args.boards, world, rank)  # the strong split of --boards
+    n_main, board0_main = (count, first) if strong_main else (args.boards, rank * args.boards)
 
     def barrier():
         if world > 1:
@@ -219,87 +235,183 @@ def run_ours(args):
             tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         return float(t.item())
 
-    # episodes long enough that no board turns terminal inside the run (num_moves is a free env parameter)
-    env = E.BatchedMatch3Env(n, 9, 9, 6, num_moves=1 << 30, env_goal=500, seed=KEY, device=dev, refill="philox",
-                             board0=rank * n)
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
+        return float(t.item())
+
+    def make_env(n, board0):
+        # episodes long enough that no board turns terminal inside the run (num_moves is a free env parameter)
+        env = E.BatchedMatch3Env(n, 9, 9, 6, num_moves=1 << 30, env_goal=500, seed=KEY, device=dev, refill="philox",
+                                 board0=board0)
+        env.board.packed_mask()
+        return env
+
+    def timed_steps(b, steps, warmup, mark_mid=False):
+        """K lockstep steps bracketed by barrier + synchronize; -> (ms max over ranks, per-step ms, per-launch ms)"""
+        for _ in range(warmup):
+            b.apply_action(None)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        two = mark_mid and b.two_kernel_step
+        # the step is TWO kernels (common-case kernel over all boards, exact kernel over the boards it hands off);
+        # ecg_step records mid[k] between them so the dominant kernel is timed by itself, live, on its own stream
+        mid = [torch.cuda.Event(enable_timing=True) for _ in range(steps)] if two else []
+        for e in mid:
+            e.record()  # creates the cudaEvent_t handles
+        torch.cuda.synchronize(dev)
+        ev[0].record()
+        for k in range(steps):
+            if two:
+                L.ecg_step_mark_event(ctypes.c_void_p(mid[k].cuda_event))
+            b.apply_action(None)  # pick + swap + cascade + reward/flags + new mask
+            ev[k + 1].record()
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms = ev[0].elapsed_time(ev[-1])
+        per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        per_launch = [ev[k].elapsed_time(mid[k]) for k in range(steps)] if two else per_step
+        return max_over_ranks(ms), per_step, per_launch
+
+    # ---- the main leg
+    env = make_env(n_main, board0_main)
     b = env.board
-    b.packed_mask()
-    for _ in range(args.warmup):
-        b.apply_action(None)
-    torch.cuda.synchronize(dev)
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    # the step is TWO kernels (common-case kernel over all boards, exact kernel over the boards it hands off);
-    # ecg_step records mid[k] between them so the dominant kernel is timed by itself, live, on its own stream
-    mid = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for e in mid:
-        e.record()  # creates the cudaEvent_t handles
-    two = b.two_kernel_step
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.ecg_launch_count()
-    torch.cuda.synchronize(dev)
-    ev[0].record()
-    for k in range(args.steps):
-        if two:
-            L.ecg_step_mark_event(ctypes.c_void_p(mid[k].cuda_event))
-        b.apply_action(None)  # pick + swap + cascade + reward/flags + new mask: 2 kernel launches
-        ev[k + 1].record()
-    torch.cuda.synchronize(dev)
-    launches = L.ecg_launch_count() - launches0
-    barrier()
+    ms_max, per_step, per_launch = timed_steps(b, args.steps, args.warmup, mark_mid=True)
+    launches = L.ecg_launch_count() - launches0 - 2 * args.warmup if b.two_kernel_step else args.steps
     clocks = sampler.stop() if sampler else None
-    ms = ev[0].elapsed_time(ev[-1])
-    per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    per_launch = [ev[k].elapsed_time(mid[k]) for k in range(args.steps)] if two else per_step
-    handed_off = int(b._scratch[0].item()) if two else 0  # of the last step
-    ms_max = max_over_ranks(ms)
-    value = world * n * args.steps / (ms_max * 1e-3)
+    handed_off = int(b._scratch[0].item()) if b.two_kernel_step else 0  # of the last step
+    n_total = sum_over_ranks(n_main)
+    value = n_total * args.steps / (ms_max * 1e-3)
     # health of the run: every board advanced every step
     stuck = int(((b.status & E.ST_NO_LEGAL) != 0).sum().item())
     bad = int(((b.status & ~E.ST_NO_LEGAL) != 0).sum().item())
     stats = E.dist.stats_dict(E.dist.reduce_stats(b.episode_stats()))
     mean_casc = float(b.cascades.float().mean().item())
+    mean_reward = float(b.step_reward.float().mean().item())
 
-    # ---- e2e through the host-buffer API
-    e2e = None
-    if not args.no_e2e:
-        hs = E.HostStepper(env, chunks=8)
+    # ---- sustained: back-to-back steps for >= 5 s, clocks and power sampled over them
+    sustained = None
+    if not args.no_extra_legs and args.sustained_seconds > 0:
+        k_sus = max(args.steps, int(args.sustained_seconds / (ms_max / args.steps * 1e-3)) + 1)
+        sampler = ClockSampler(local) if rank == 0 else None
+        ms_sus, _, _ = timed_steps(b, k_sus, 0)
+        c = sampler.stop() if sampler else {}
+        sustained = {"value": n_total * k_sus / (ms_sus * 1e-3), "unit": UNIT, "steps": k_sus,
+                     "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / k_sus, "sm_mhz_median": c.get("sm_mhz"),
+                     "sm_mhz_min": c.get("sm_mhz_min"), "power_w_median": c.get("power_w_median"),
+                     "reasons": c.get("reasons"), "clock_samples": c.get("samples"),
+                     "vs_burst": (n_total * k_sus / (ms_sus * 1e-3)) / value}
+
+    # ---- e2e through the host-buffer API: the env contract (uint8 cells) and the 4-bit form
+    def e2e_leg(fmt):
+        hs = E.HostStepper(env, chunks=8, obs_format=fmt)
         for _ in range(2):
             hs.step(hs.random_action())
         torch.cuda.synchronize(dev)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            a = hs.random_action()          # D2H: 4 B/board
-            hs.step(a)                      # H2D: 4 B/board; D2H: obs 81 + reward 4 + done 1 + won 1 B/board
+            a = hs.random_action()          # D2H: the action the host sends back in
+            hs.step(a)                      # H2D: actions; D2H: obs, reward, done, won
         torch.cuda.synchronize(dev)
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        e2e = {"value": world * n * args.e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes + n * 4,
-               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-               "api": "HostStepper.random_action() + HostStepper.step(actions_host) -> (obs u8, reward, done, won) "
-                      "in pinned host memory, 8 chunks pipelined over CUDA streams"}
+        d2h = hs.d2h_bytes + hs.action_d2h_bytes
+        out = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "obs_format": fmt, "d2h_bytes_per_board": d2h / n_main,
+               "pcie_d2h_gb_s_per_gpu": d2h * args.e2e_steps / dt / 1e9,
+               "pcie_d2h_gb_s_all_gpus": sum_over_ranks(d2h) * args.e2e_steps / dt / 1e9,
+               "api": "HostStepper.random_action() + HostStepper.step(actions_host) -> (obs, reward, done, won) in "
+                      "pinned host memory, 8 chunks pipelined over CUDA streams; obs = " +
+                      ("uint8 [N,9,9] cell values, int32 reward/actions (the env contract)" if fmt == "uint8" else
+                       "uint8 [N,41] 4-bit cell codes (ecg_unpack_nibbles), int16 reward/actions")}
         del hs
+        return out
+
+    e2e = e2e_nib = None
+    if not args.no_e2e:
+        e2e = e2e_leg("uint8")
+        e2e_nib = e2e_leg("nibbles")
+
+    env = b = None  # the main batch is done: free its 1.6 GB before the other legs allocate theirs
+    torch.cuda.empty_cache()
+
+    # ---- the other scaling mode on the same K steps
+    twin = None
+    if not args.no_extra_legs:
+        if world == 1:
+            twin = {"value": value, "ms_per_step": ms_max / args.steps, "boards_total": n_main,
+                    "note": "N = 1: weak and strong are the same run"}
+        else:
+            n2, b02 = (args.boards, rank * args.boards) if strong_main else (count, first)
+            env2 = make_env(n2, b02)
+            ms2, _, _ = timed_steps(env2.board, args.steps, args.warmup)
+            tot2 = sum_over_ranks(n2)
+            twin = {"value": tot2 * args.steps / (ms2 * 1e-3), "ms_per_step": ms2 / args.steps, "boards_total": int(tot2),
+                    "boards_per_gpu": n2}
+            env2 = None
+            torch.cuda.empty_cache()
+
+    # ---- the reference's dynamics: every step restarts the MT19937 stream of cfg.seed (boardv2.py:46)
+    replay = None
+    if not args.no_extra_legs and args.replay_steps > 0:
+        replay = {}
+        seed = 20261019
+        src = E.BatchedBoards(E.BoardConfig(seed=seed), n_main, 1 << 30, device=dev, key=KEY, board0=board0_main)
+        for name, streams in (("shared_stream", 1), ("streams_4096", 4096)):
+            kw = dict(seeds=[seed]) if streams == 1 else dict(
+                seeds=[seed + i for i in range(streams)],
+                stream_index=(torch.arange(n_main, device=dev, dtype=torch.int64) + board0_main).remainder(streams))
+            rb = E.BatchedBoards(E.BoardConfig(seed=seed), n_main, 1 << 30, device=dev, refill="replay",
+                                 stream_len=2048, env_goal=500, **kw)
+            rb.boards.copy_(src.boards)  # distinct boards (Philox-drawn, no match on them), replayed refills and picks
+            rb._mask_valid = False
+            rb.packed_mask()
+            ms_r, _, _ = timed_steps(rb, args.replay_steps, 3)
+            overflow = int(((rb.status & E.ST_STREAM_OVERFLOW) != 0).sum().item())
+            replay[name] = {"value": n_total * args.replay_steps / (ms_r * 1e-3), "unit": UNIT,
+                            "ms_per_step": ms_r / args.replay_steps, "steps": args.replay_steps, "streams": streams,
+                            "mean_cascades_per_step": float(rb.cascades.float().mean().item()),
+                            "mean_reward_per_step": float(rb.step_reward.float().mean().item()),
+                            "boards_with_stream_overflow": overflow}
+            del rb
+            torch.cuda.empty_cache()
+        del src
+        replay["kernel"] = ("lane_kernel<Shape<9,9,3,false>, replay, step, exact> (one launch per step: the exact build, "
+                            "refill tiles and picks by numpy's masked rejection over the raw MT19937 words in HBM)")
+        replay["philox_for_comparison"] = {"mean_cascades_per_step": mean_casc, "mean_reward_per_step": mean_reward}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_rate(12.0)
+        cpu["python_reference"] = ("absent on this box: the reference is pure Python under /root/reference of the "
+                                   "authoring container and cannot travel; measured there: see BASELINE.md / DESIGN.md")
 
     if rank == 0:
         peak, peak_src = measured_peak()
         avg_launch_ms = sum(per_launch) / len(per_launch)
         avg_step_ms = sum(per_step) / len(per_step)
-        finished = n - handed_off  # env-steps the dominant kernel completes per launch
+        finished = n_main - handed_off  # env-steps the dominant kernel completes per launch
         achieved = BYTES_PER_STEP * finished / (avg_launch_ms * 1e-3) / 1e9
         traffic = ncu_traffic()
+        per_gpu = n_main
+        scale_traffic = per_gpu / traffic["boards_per_launch"] if traffic and traffic.get("boards_per_launch") else 1.0
+        cfg = workload(args.boards if not strong_main else n_main, world)
+        cfg["scaling_mode"] = args.scaling
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload(n, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": cfg, "clocks": clocks, "e2e": e2e, "e2e_nibbles": e2e_nib, "gpu_launches": int(launches),
+            ("weak" if strong_main else "strong"): twin, "sustained": sustained, "replay": replay,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                         "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch") * scale_traffic,
+                         "traffic_source": None if traffic is None else traffic.get("source"),
                          "kernel": "lane_kernel<Shape<9,9,3,false>, philox, step, FAST> (common-case kernel of the "
                                    "two-kernel step: persistent warp loop, free-running warps)",
                          "algorithmic_bytes_per_launch": BYTES_PER_STEP * finished, "avg_launch_ms": avg_launch_ms,
@@ -311,12 +423,11 @@ def run_ours(args):
                              "issue_slots_pct_busy": traffic.get("issue_slots_pct_busy"),
                              "active_threads_per_instruction": traffic.get("active_threads_per_instruction"),
                              "source": "ncu capture of this kernel, profiles/step_kernel_traffic.json"},
-                         "note": "integer-ALU-pipe bound, not HBM bound (DESIGN.md section 5): ~1700 integer "
-                                 "thread-instructions per env-step against 117 B; ncu: ALU pipe 88 % of peak, issue slots "
-                                 "61 % busy at 18.2 of 32 threads active, DRAM 16 %"},
+                         "note": "integer-ALU-pipe bound, not HBM bound (DESIGN.md section 5): the ncu figures above "
+                                 "are from the committed capture of this kernel, not from this run"},
             "cpu_baseline": cpu,
-            "run": {"mean_cascades_per_step": mean_casc, "boards_without_legal_move": stuck, "boards_flagged": bad,
-                    "episode_stats": stats},
+            "run": {"mean_cascades_per_step": mean_casc, "mean_reward_per_step": mean_reward,
+                    "boards_without_legal_move": stuck, "boards_flagged": bad, "episode_stats": stats},
         }
         print(json.dumps(line))
     if world > 1:

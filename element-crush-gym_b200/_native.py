@@ -56,6 +56,7 @@ EXPORTS = {
     "ecg_masks_bytes": (C.c_int64, [C.POINTER(Config), C.c_int64]),
     "ecg_pack": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_unpack": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "ecg_unpack_nibbles": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_unpack_mask": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_mt19937_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "ecg_init_boards": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -34,12 +34,13 @@ class BatchedBoards:
         (key, board0 + i, step) -- results do not depend on how the batch is sharded over GPUs.
     refill="replay": board i replays numpy's legacy MT19937 stream of seeds[i] exactly like the
         reference (np.random.seed(cfg.seed) at the top of every apply_action, boardv2.py:46), which
-        makes trajectories bit-identical to BoardV2 / samplerTasks.random_task.
+        makes trajectories bit-identical to BoardV2 / samplerTasks.random_task.  One seed = one stream
+        shared by all boards (every state of one BoardConfig); stream_index[i] picks among len(seeds) streams.
     """
 
     def __init__(self, cfg: BoardConfig, num_boards: int, n_actions: int = 20, *, device=None, refill="philox",
                  key=None, seeds=None, board0: int = 0, stream_len: int = 4096, arrays=None,
-                 env_goal: int = _I32_MAX, _empty=False):
+                 env_goal: int = _I32_MAX, stream_index=None, _empty=False):
         if not torch.cuda.is_available():
             raise N.EcgError("BatchedBoards needs a CUDA device (no CPU fallback)")
         self.L = N.lib()
@@ -80,15 +81,19 @@ class BatchedBoards:
             if seeds is None:
                 seeds = [cfg.seed] * 1  # one shared stream: every board replays cfg.seed (MCTS leaves do)
             seeds_t = torch.as_tensor(seeds, dtype=torch.int64).reshape(-1)
-            if seeds_t.numel() not in (1, self.n):
-                raise ValueError("seeds must hold one seed (shared stream) or one per board")
+            if stream_index is not None:  # any number of streams, board i replays stream stream_index[i]
+                self.stream_index = torch.as_tensor(stream_index).to(device=dev, dtype=torch.int32).contiguous()
+                if self.stream_index.numel() != self.n:
+                    raise ValueError("stream_index must hold one stream id per board")
+            elif seeds_t.numel() not in (1, self.n):
+                raise ValueError("seeds must hold one seed (shared stream) or one per board (or pass stream_index)")
             self.seeds = seeds_t.clone()
             sd = seeds_t.to(dev).to(torch.int32)
             self.stream_len = int(stream_len)
             self.stream = torch.empty(sd.numel() * self.stream_len, dtype=torch.int32, device=dev)
             N.check(self.L.ecg_mt19937_stream(_ptr(sd), _ptr(self.stream), self.stream_len, sd.numel(), _stream(dev)),
                     "ecg_mt19937_stream")
-            self.stream_stride = self.stream_len if sd.numel() == self.n and self.n > 1 else 0
+            self.stream_stride = self.stream_len if (sd.numel() == self.n and self.n > 1) or stream_index is not None else 0
             self.stream_pos = torch.zeros(self.n, dtype=torch.int32, device=dev)
         elif refill != "philox":
             raise ValueError("refill must be 'philox' or 'replay'")

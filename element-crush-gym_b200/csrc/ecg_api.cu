@@ -218,6 +218,15 @@ int ecg_unpack(const ecg_config *cfg, const void *boards, void *cells, int elem_
     return check_launch("ecg_unpack");
 }
 
+int ecg_unpack_nibbles(const ecg_config *cfg, const void *boards, uint8_t *out, int64_t n, void *stream) {
+    if (check_cfg(cfg)) return -1;
+    if (!out || !boards) return fail("ecg_unpack_nibbles: NULL buffer");
+    if (reinterpret_cast<uintptr_t>(out) & 3u) return fail("ecg_unpack_nibbles: out must be 4-byte aligned");
+    if (n <= 0) return 0;
+    ops_for(cfg->rows)->unpack_nibbles(boards, out, n, (cudaStream_t)stream);
+    return check_launch("ecg_unpack_nibbles");
+}
+
 int ecg_unpack_mask(const ecg_config *cfg, const uint32_t *mask, uint8_t *out, int64_t n, void *stream) {
     if (check_cfg(cfg)) return -1;
     if (!mask || !out) return fail("ecg_unpack_mask: NULL buffer");

@@ -42,6 +42,7 @@ struct ShapeOps {
     void (*pack)(bool wide, const void *cells, int elem_bytes, void *boards, uint8_t *status, int types, long long n,
                  cudaStream_t s);
     void (*unpack)(bool wide, const void *boards, void *cells, int elem_bytes, int types, long long n, cudaStream_t s);
+    void (*unpack_nibbles)(const void *boards, uint8_t *out, long long n, cudaStream_t s);
     void (*unpack_mask)(const uint32_t *mask, uint8_t *out, long long n, cudaStream_t s);
     void (*init)(bool wide, bool philox, RefillDev rf, void *boards, uint8_t *status, int types, long long n,
                  cudaStream_t s);

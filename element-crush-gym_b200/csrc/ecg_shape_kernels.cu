@@ -191,6 +191,58 @@ __global__ void __launch_bounds__(BLOCK) unpack_kernel(const void *boards, T *__
     }
 }
 
+// The compact observation: 4-bit cell CODES (0 empty, 1..11 plain token, 12 h_line, 13 v_line, 14 bomb, 15 mega),
+// row-major, two cells per byte (cell 2k in the low nibble of byte k), ceil(R*C/2) bytes per board, boards back to
+// back.  Same staging as unpack_kernel; a lane's 32-bit store carries 8 cells, and a word may span two boards.
+template <class SH>
+__global__ void __launch_bounds__(BLOCK) unpack_nibbles_kernel(const void *boards, uint8_t *__restrict__ out,
+                                                               long long n) {
+    using G = typename SH::G;
+    constexpr int BW = 4 * G::W, RC = G::R * G::C, NBY = (RC + 1) / 2;
+    static_assert((32 * NBY) % 4 == 0, "a tile's output is a whole number of words");
+    __shared__ uint32_t tile_words[BLOCK / 32][32 * BW];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long tile = (long long)blockIdx.x * (BLOCK / 32) + wib;
+    if (tile * 32 >= n) return;
+    uint32_t *tw = tile_words[wib];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(boards) + tile * (BW / 4 * 32);
+#pragma unroll
+        for (int k = 0; k < BW / 4; k++) reinterpret_cast<uint4 *>(tw)[k * 32 + lane] = src[k * 32 + lane];
+    }
+    __syncwarp();
+    const long long rest = n - tile * 32;
+    const int total = (int)(rest < 32 ? rest : 32) * NBY; // bytes of this tile
+    uint8_t *dst = out + tile * 32 * NBY;
+    for (int y0 = lane * 4; y0 < total; y0 += 32 * 4) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int y = y0 + v;
+            const int b = y / NBY, k = y - b * NBY;
+            uint32_t byte = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int idx = 2 * k + h;
+                if (idx < RC) {
+                    const int r = idx / G::C, c = idx - r * G::C, bit = r * G::S + c;
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const int j = p * G::W + (bit >> 5);
+                        byte |= ((tw[((j >> 2) * 32 + b) * 4 + (j & 3)] >> (bit & 31)) & 1u) << (4 * h + p);
+                    }
+                }
+            }
+            packed |= byte << (8 * v);
+        }
+        if (y0 + 4 <= total) {
+            *reinterpret_cast<uint32_t *>(dst + y0) = packed;
+        } else {
+            for (int v = 0; y0 + v < total; v++) dst[y0 + v] = (uint8_t)(packed >> (8 * v));
+        }
+    }
+}
+
 template <class SH, typename T>
 __global__ void __launch_bounds__(BLOCK) unpack_kernel_simple(const void *boards, T *__restrict__ cells, int types,
                                                               long long n) {
@@ -672,6 +724,9 @@ void op_unpack(bool wide, const void *boards, void *cells, int eb, int types, lo
         else unpack_kernel_simple<SHN, uint8_t><<<g1, BLOCK, 0, s>>>(boards, (uint8_t *)cells, types, n);
     }
 }
+void op_unpack_nibbles(const void *boards, uint8_t *out, long long n, cudaStream_t s) {
+    unpack_nibbles_kernel<SHN><<<grid_for((n + 31) / 32, BLOCK / 32), BLOCK, 0, s>>>(boards, out, n);
+}
 void op_unpack_mask(const uint32_t *mask, uint8_t *out, long long n, cudaStream_t s) {
     unpack_mask_kernel<SHN><<<grid_for(n * SHN::G::A, BLOCK), BLOCK, 0, s>>>(mask, out, n);
 }
@@ -778,7 +833,7 @@ void op_augment(const void *boards_in, void *boards_out, bool mirror, bool remap
     augment_kernel<SHN><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(boards_in, boards_out, mirror, remap, lut, n);
 }
 
-const ShapeOps k_ops = {op_pack, op_unpack, op_unpack_mask, op_init, op_legal, op_random_action, op_step, op_rollout,
+const ShapeOps k_ops = {op_pack, op_unpack, op_unpack_nibbles, op_unpack_mask, op_init, op_legal, op_random_action, op_step, op_rollout,
                         op_onehot, op_augment};
 
 } // namespace

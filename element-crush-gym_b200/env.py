@@ -92,10 +92,20 @@ class HostStepper:
     """The public call with HOST buffers: actions come from pinned host memory, observation, reward, done
     and won go back to pinned host memory every step.  The batch is cut into chunks whose H2D copy, step
     kernel and D2H copies run on separate CUDA streams so PCIe transfers overlap the kernels.
-    bench.py's e2e number is measured through this class."""
+    bench.py's e2e number is measured through this class.
 
-    def __init__(self, env: BatchedMatch3Env, chunks: int = 8):
+    obs_format="uint8" (default, the env contract): observation uint8 [N, H, W] of cell VALUES, reward int32,
+        actions int32 -- 4 B in and H*W + 6 B out per board and step.
+    obs_format="nibbles": the same information in about half the PCIe bytes (PCIe is the whole e2e cost: the step
+        kernel is 20x faster than the copies): observation uint8 [N, ceil(H*W/2)] of 4-bit cell CODES
+        (ecg_unpack_nibbles; `decode_obs` turns it into the uint8 form on the host when wanted), reward int16
+        (saturating), actions int16."""
+
+    def __init__(self, env: BatchedMatch3Env, chunks: int = 8, obs_format: str = "uint8"):
+        if obs_format not in ("uint8", "nibbles"):
+            raise ValueError("obs_format must be 'uint8' or 'nibbles'")
         self.env = env
+        self.obs_format = obs_format
         n = env.num_envs
         self.n = n
         dev = env.board.device
@@ -107,24 +117,31 @@ class HostStepper:
         self.streams = [torch.cuda.Stream(device=dev) for _ in self.bounds]
         R, Cc = env.height, env.width
         pin = dict(pin_memory=True)
-        self.h_actions = torch.zeros(n, dtype=torch.int32, **pin)
-        self.h_obs = torch.zeros((n, R, Cc), dtype=torch.uint8, **pin)
-        self.h_reward = torch.zeros(n, dtype=torch.int32, **pin)
+        nib = obs_format == "nibbles"
+        small = torch.int16 if nib else torch.int32
+        obs_shape = (n, (R * Cc + 1) // 2) if nib else (n, R, Cc)
+        self.h_actions = torch.zeros(n, dtype=small, **pin)
+        self.h_obs = torch.zeros(obs_shape, dtype=torch.uint8, **pin)
+        self.h_reward = torch.zeros(n, dtype=small, **pin)
         self.h_done = torch.zeros(n, dtype=torch.bool, **pin)
         self.h_won = torch.zeros(n, dtype=torch.bool, **pin)
         self.d_actions = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.d_obs = torch.zeros((n, R, Cc), dtype=torch.uint8, device=dev)
+        self.d_actions_in = torch.zeros(n, dtype=small, device=dev) if nib else self.d_actions
+        self.d_reward = torch.zeros(n, dtype=small, device=dev) if nib else None
+        self.d_tmp32 = torch.zeros(n, dtype=torch.int32, device=dev) if nib else None
+        self.d_obs = torch.zeros(obs_shape, dtype=torch.uint8, device=dev)
         # done / won as 0/1 bytes, split from the flags byte on the device: a host-side pass over N flags per step would
         # cost more than the copy (and torchrun pins the host side to one thread)
         self.d_done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.d_won = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.scratch = (torch.empty(n + len(self.bounds), dtype=torch.int32, device=dev)
                         if env.board.two_kernel_step else None)
-        self.h2d_bytes = n * 4
-        self.d2h_bytes = n * (R * Cc + 4 + 2)
+        a_bytes = 2 if nib else 4
+        self.h2d_bytes = n * a_bytes
+        self.d2h_bytes = n * (self.h_obs[0].numel() + a_bytes + 2)
+        self.action_d2h_bytes = n * a_bytes  # random_action(): the pick the host sends back in
 
     def _chunk_call(self, lo, hi, fn_step):
-        import ctypes as C
         b = self.env.board
         nat = b.nat
         bw, mw = nat.board_words, nat.mask_words
@@ -155,24 +172,35 @@ class HostStepper:
         return io, rf
 
     def step(self, actions_host: torch.Tensor = None):
-        """actions_host: pinned int32 [N] (defaults to self.h_actions).  Returns the pinned host tensors
-        (obs uint8 [N,H,W], reward int32 [N], done bool [N], won bool [N], {}) after a full sync."""
+        """actions_host: pinned int32 (int16 with obs_format="nibbles") [N]; defaults to self.h_actions.  Returns the
+        pinned host tensors (obs, reward, done bool [N], won bool [N], {}) after a full sync."""
         import ctypes as C
         env, b = self.env, self.env.board
         L = b.L
+        nib = self.obs_format == "nibbles"
         src = self.h_actions if actions_host is None else actions_host
         cur = torch.cuda.current_stream(self.dev)
         for (lo, hi), st in zip(self.bounds, self.streams):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                self.d_actions[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                self.d_actions_in[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                if nib:
+                    self.d_actions[lo:hi].copy_(self.d_actions_in[lo:hi])  # int16 -> int32 on the device
                 io, rf = self._chunk_call(lo, hi, None)
                 sp = C.c_void_p(st.cuda_stream)
                 N.check(L.ecg_step(C.byref(b.nat), C.byref(rf), C.byref(io), hi - lo, sp), "ecg_step")
-                N.check(L.ecg_unpack(C.byref(b.nat), C.c_void_p(b.boards[lo * b.nat.board_words:].data_ptr()),
-                                     C.c_void_p(self.d_obs[lo:].data_ptr()), 1, hi - lo, sp), "ecg_unpack")
+                boards = C.c_void_p(b.boards[lo * b.nat.board_words:].data_ptr())
+                if nib:
+                    N.check(L.ecg_unpack_nibbles(C.byref(b.nat), boards, C.c_void_p(self.d_obs[lo:].data_ptr()),
+                                                 hi - lo, sp), "ecg_unpack_nibbles")
+                    torch.clamp(b.step_reward[lo:hi], max=32767, out=self.d_tmp32[lo:hi])  # saturate, then narrow
+                    self.d_reward[lo:hi].copy_(self.d_tmp32[lo:hi])
+                    self.h_reward[lo:hi].copy_(self.d_reward[lo:hi], non_blocking=True)
+                else:
+                    N.check(L.ecg_unpack(C.byref(b.nat), boards, C.c_void_p(self.d_obs[lo:].data_ptr()), 1, hi - lo,
+                                         sp), "ecg_unpack")
+                    self.h_reward[lo:hi].copy_(b.step_reward[lo:hi], non_blocking=True)
                 self.h_obs[lo:hi].copy_(self.d_obs[lo:hi], non_blocking=True)
-                self.h_reward[lo:hi].copy_(b.step_reward[lo:hi], non_blocking=True)
                 torch.bitwise_and(b.flags[lo:hi], N.FLAG_DONE, out=self.d_done[lo:hi])
                 torch.bitwise_right_shift(b.flags[lo:hi], 1, out=self.d_won[lo:hi])  # FLAG_WON == 2, the top flag
                 self.h_done[lo:hi].copy_(self.d_done[lo:hi].view(torch.bool), non_blocking=True)
@@ -182,14 +210,29 @@ class HostStepper:
         cur.synchronize()
         b._mask_valid = True
         b.step_ctr += 1
+        b._moves_bound = max(b._moves_bound - 1, 0)
         return self.h_obs, self.h_reward, self.h_done, self.h_won, {}
 
     def random_action(self) -> torch.Tensor:
-        """board.random_action() with the result copied to pinned host memory (int32 [N])"""
+        """board.random_action() with the result copied to pinned host memory (int32 / int16 [N])"""
         a = self.env.board.random_action(out=self.d_actions)
+        if self.obs_format == "nibbles":
+            self.d_actions_in.copy_(a)
+            a = self.d_actions_in
         self.h_actions.copy_(a, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         return self.h_actions
+
+    def decode_obs(self, obs_nibbles=None) -> np.ndarray:
+        """host side, optional: the nibble observation -> uint8 [N, H, W] of cell values (BoardV2.array as uint8)"""
+        cfg = self.env.cfg
+        x = (self.h_obs if obs_nibbles is None else obs_nibbles).numpy()
+        lut = np.array(list(range(12)) + [cfg.h_line, cfg.v_line, cfg.bomb, cfg.mega_token], dtype=np.uint8)
+        cells = np.empty((x.shape[0], x.shape[1] * 2), dtype=np.uint8)
+        cells[:, 0::2] = lut[x & 15]
+        cells[:, 1::2] = lut[x >> 4]
+        R, Cc = self.env.height, self.env.width
+        return cells[:, :R * Cc].reshape(-1, R, Cc)
 
 
 class Match3Env:

@@ -2,14 +2,30 @@
 
 Host-side tree exactly as mctslib/abc/mcts.py:33-130 + mctslib/standard/mcts.py:9-42 (UCB1 with
 c = node.state.n_actions, expansion pops the largest untried action, most-visited child is played, the tree
-is re-rooted at it), but the simulation step evaluates the expanded node with `leaves` independent random
-rollouts in ONE kernel launch (ecg_rollout) instead of one Python rollout; back-propagation then adds
-`leaves` visits and the sum of their final rewards.  With several ranks every rank rolls out its share and the
-(visits, reward sum) pair is all-reduced over NCCL (dist.reduce_visit_counts) -- the only communication.
+is re-rooted at it; pinned against the reference's own tree by tests/golden/mcts_tree.json), but the simulation
+step evaluates the expanded node with `leaves` random rollouts instead of one Python rollout; back-propagation
+then adds `leaves` visits and the sum of their final rewards.  With several ranks every rank rolls out its share
+and the (reward sum, env-steps) pair is all-reduced over NCCL (dist.reduce_visit_counts) -- the only
+communication.  The tree policy needs every simulation's value before the next selection, so there is exactly one
+device-to-host read per simulation (the reduced reward sum); visit counts are known on the host.
 
-Rollouts use the Philox mode: like the reference's non-deterministic MCTS (standard/mcts.py:15 seeds from
-`random`), results are statistically, not bit-wise, comparable with the reference; against the CPU oracle's
-Philox episodes they are bit-exact (tests/test_gpu_mcts.py).
+Two rollout dynamics:
+
+refill="philox" (default, the throughput mode): `leaves` INDEPENDENT episodes in one ecg_rollout launch, refill
+    tiles and picks from Philox substreams.  This is NOT the reference's rollout distribution: the reference reseeds
+    the refill generator with cfg.seed at every step (boardv2.py:46), which makes its steps cascade longer --
+    measured on 9x9x6, 20-move random episodes: 1.79-1.81 cascade iterations and 24.4 reward per step with the
+    reference's semantics against 1.55 and 17.3 with i.i.d. Philox tiles; episode reward 476 +- 231 against
+    345 +- 144.  Bit-exact against the CPU oracle's Philox episodes (tests/test_gpu_mcts.py), not comparable
+    with the reference's values.
+
+refill="replay" (the reference's dynamics, A12): mctslib/standard/mcts.py:14-19 seeds numpy from Python's `random`,
+    draws the FIRST action with it, and from then on every pick and every refill comes from the MT19937 stream of
+    cfg.seed, restarted by each apply_action -- a rollout is a deterministic function of its first action.  The
+    engine therefore plays every legal first action once (one expansion launch + one ecg_rollout launch on the
+    shared MT(cfg.seed) stream, bit-exact with the reference's episodes) and draws the `leaves` first picks
+    uniformly over them; `deterministic=True` takes the first pick from MT(cfg.seed) as the reference intended
+    (its `state.seed` does not exist, standard/mcts.py:15).
 """
 from __future__ import annotations
 
@@ -71,11 +87,10 @@ class Node:
 
 def replicate(state: BoardV2, n: int, *, key: int, board0: int, device=None) -> BatchedBoards:
     """n copies of one board as a Philox-mode batch (copy i is global board board0 + i)."""
-    src = state._b
-    out = BatchedBoards(state.cfg, n, state.n_actions, device=device or src.device, refill="philox", key=key,
+    out = BatchedBoards(state.cfg, n, state.n_actions, device=device or state.device, refill="philox", key=key,
                         board0=board0, _empty=True)
     words = state.cfg.native.board_words
-    tile = src.boards[: 32 * words].view(words // 4, 32, 4)  # [chunk, lane, 4 words]; the board sits in lane 0
+    tile = state._boards.view(words // 4, 32, 4)  # [chunk, lane, 4 words]; the board sits in lane 0
     full = tile[:, :1, :].expand(words // 4, 32, 4).reshape(-1)  # the same board in all 32 lanes
     out.boards.view(-1, 32 * words)[:] = full
     return out
@@ -85,7 +100,9 @@ class BatchedRolloutMCTS:
     """Same call shape as mctslib.standard.mcts.MCTS: `action, value, policies = mcts()`."""
 
     def __init__(self, state: BoardV2, exploration_weight: float, simulations: int, verbose: bool = False,
-                 deterministic: bool = False, *, leaves: int = 1 << 20, key: int = 0x5EED):
+                 deterministic: bool = False, *, leaves: int = 1 << 20, key: int = 0x5EED, refill: str = "philox"):
+        if refill not in ("philox", "replay"):
+            raise ValueError("refill must be 'philox' or 'replay'")
         self._root = Node(state)
         self._simulations = simulations
         self._verbose = verbose
@@ -93,9 +110,39 @@ class BatchedRolloutMCTS:
         self.deterministic = deterministic
         self.leaves = int(leaves)
         self.key = int(key)
+        self.refill = refill
         self._sim_counter = 0
-        self.env_steps = 0
+        self._steps_dev = None  # env-steps simulated on this rank, accumulated on the device
         self._root.expand()  # abc/mcts.py:82
+
+    @property
+    def env_steps(self) -> int:
+        """env-steps simulated on the device so far, over all ranks (one read; not on the search path)"""
+        if self._steps_dev is None:
+            return 0
+        t = self._steps_dev.clone()
+        ecg_dist.reduce_visit_counts(t, t.new_zeros(1))
+        return int(t.item())
+
+    def _count_steps(self, steps: torch.Tensor):
+        s = steps.sum().to(torch.int64).reshape(1)
+        self._steps_dev = s if self._steps_dev is None else self._steps_dev + s
+
+    def _first_action_returns(self, state: BoardV2) -> torch.Tensor:
+        """refill="replay": final cumulative reward of the reference's rollout for every legal first action of
+        `state`, int64 [L] on the device (standard/mcts.py:16-18 over boardv2.py:46)."""
+        legal = state.legal_actions
+        dev = state.device
+        n = len(legal)
+        acts = torch.tensor(legal, dtype=torch.int32).to(dev)
+        boards, mask, res = state._step(acts, n, torch.zeros(n, dtype=torch.int32, device=dev))
+        rest = BatchedBoards(state.cfg, n, state.n_actions - 1, device=dev, refill="replay", _empty=True)
+        rest.stream, rest.stream_len, rest.stream_stride = state._stream, state.stream_len, 0  # MT(cfg.seed), shared
+        rest.stream_pos = res[3].contiguous()  # each episode continues where its first step left the stream
+        rest.boards = boards
+        total = rest.rollout()
+        self._count_steps(rest.rollout_steps + 1)
+        return total + res[0].to(torch.int64) + int(state.reward)
 
     def rollout(self, state: BoardV2):
         """-> (sum of final rewards, number of rollouts) over all ranks"""
@@ -103,20 +150,31 @@ class BatchedRolloutMCTS:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         first, count = ecg_dist.shard_range(self.leaves, world, rank)
-        base = self._sim_counter * self.leaves
+        sim = self._sim_counter
         self._sim_counter += 1
-        dev = state._b.device
-        if count > 0 and not state.is_terminal:
-            batch = replicate(state, count, key=self.key, board0=base + first)
+        dev = state.device
+        if count == 0 or state.is_terminal or (self.refill == "replay" and not state.legal_actions):
+            rsum = torch.tensor([int(state.reward) * count], dtype=torch.int64, device=dev)
+        elif self.refill == "philox":
+            batch = replicate(state, count, key=self.key, board0=sim * self.leaves + first)
             total = batch.rollout()
-            rsum = total.sum() + state.reward * count
-            self.env_steps += int(batch.rollout_steps.sum().item())
+            self._count_steps(batch.rollout_steps)
+            rsum = (total.sum() + int(state.reward) * count).reshape(1)
         else:
-            rsum = torch.tensor(state.reward * count, dtype=torch.int64, device=dev)
-        visits = torch.tensor([count], dtype=torch.int64, device=dev)
-        rsum = rsum.reshape(1).to(torch.int64)
+            returns = self._first_action_returns(state)  # [L]
+            n = returns.numel()
+            if self.deterministic:  # np.random.seed(cfg.seed); np.random.choice(legal): one fixed first pick
+                import numpy as np
+                picks = torch.zeros(n, dtype=torch.int64, device=dev)
+                picks[int(np.random.RandomState(state.cfg.seed).choice(n))] = count
+            else:  # the reference seeds this pick from Python's `random`: uniform over the legal set
+                g = torch.Generator(device="cpu")
+                g.manual_seed((self.key * 1000003 + sim * 8191 + rank) & (2 ** 63 - 1))
+                picks = torch.bincount(torch.randint(n, (count,), generator=g), minlength=n).to(dev)
+            rsum = (picks * returns).sum().reshape(1)
+        visits = torch.zeros(1, dtype=torch.int64, device=dev)  # known on the host: nothing to reduce or read
         ecg_dist.reduce_visit_counts(visits, rsum)
-        return int(rsum.item()), int(visits.item())
+        return int(rsum.item()), self.leaves
 
     def __call__(self):
         node = self._root

@@ -128,6 +128,11 @@ int ecg_pack(const ecg_config *cfg, const void *cells, int elem_bytes, void *boa
              void *stream);
 /* packed -> BoardV2.array (the env's observation, env.py:56) */
 int ecg_unpack(const ecg_config *cfg, const void *boards, void *cells, int elem_bytes, int64_t n, void *stream);
+/* packed -> the compact observation: 4-bit cell CODES (0 empty, 1..11 plain token of that type, 12 h_line, 13 v_line,
+ * 14 bomb, 15 mega_token), row-major, two cells per byte (cell 2k in the low nibble of byte k), ceil(rows*cols/2)
+ * bytes per board, boards back to back: BoardV2.array at half the bytes of the uint8 form (env.py:56 observation for
+ * callers that cross PCIe).  out must be 4-byte aligned. */
+int ecg_unpack_nibbles(const ecg_config *cfg, const void *boards, uint8_t *out, int64_t n, void *stream);
 /* packed legal mask -> [n, action_space] bytes (1 = legal): membership form of BoardV2.legal_actions */
 int ecg_unpack_mask(const ecg_config *cfg, const uint32_t *mask, uint8_t *out, int64_t n, void *stream);
 

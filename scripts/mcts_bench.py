@@ -21,12 +21,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--leaves", type=int, default=1 << 20)
 ap.add_argument("--sims", type=int, default=32)
 ap.add_argument("--moves", type=int, default=20)
+ap.add_argument("--refill", default="philox", choices=["philox", "replay"])
 a = ap.parse_args()
 rank, world, local = E.dist.init_from_env()
 torch.cuda.set_device(local)
 cfg = E.BoardConfig(seed=7)
 state = E.BoardV2(a.moves, cfg, device=f"cuda:{local}")
-m = E.BatchedRolloutMCTS(state, 3, 4, False, leaves=a.leaves, key=1234)
+m = E.BatchedRolloutMCTS(state, 3, 4, False, leaves=a.leaves, key=1234, refill=a.refill)
 m()  # warm-up: 4 simulations (also re-roots the tree, like the reference's move loop)
 m._simulations = a.sims
 torch.cuda.synchronize()
@@ -37,18 +38,17 @@ t0 = time.perf_counter()
 action, value, policies = m()
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-steps = torch.tensor([m.env_steps - steps0], dtype=torch.int64, device=f"cuda:{local}")
+steps = m.env_steps - steps0  # already summed over the ranks
 tmax = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
 if world > 1:
-    torch.distributed.all_reduce(steps)
     torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
 if rank == 0:
     dt = float(tmax.item())
     print(json.dumps({"config": "mctslib standard MCTS, 9x9x6, GPU-batched rollouts", "n_gpus": world,
                       "leaves_per_simulation": a.leaves, "simulations": a.sims, "moves": a.moves,
                       "ms_per_simulation": dt / a.sims * 1e3, "leaves_per_s": a.leaves * a.sims / dt,
-                      "rollout_env_steps_per_s": int(steps.item()) / dt, "action": int(action), "value": int(value),
+                      "rollout_env_steps_per_s": steps / dt, "refill": a.refill, "action": int(action), "value": int(value),
                       "root_children": len(policies),
-                      "reduction": "NCCL all-reduce of (visits, reward sum) per simulation" if world > 1 else "none"}))
+                      "reduction": "NCCL all-reduce of the reward sum per simulation (visit counts are known on the host)" if world > 1 else "none"}))
 if world > 1:
     torch.distributed.destroy_process_group()

@@ -290,36 +290,72 @@ def test_match3env_dropin_contract(E):
     assert np.array_equal(obs2, d["init"][e])  # env.py:62: reset() without a seed keeps the seed
 
 
-def test_host_stepper_matches_device_api(E):
+@pytest.mark.parametrize("obs_format", ["uint8", "nibbles"])
+def test_host_stepper_matches_device_api(E, obs_format):
     """HostStepper (host buffers in pinned memory, chunked over CUDA streams: the call bench.py's e2e times) returns
     the same observations, rewards and done / won flags as BatchedMatch3Env.step on a twin environment, and both
-    match the oracle (Philox mode, ragged chunk sizes)."""
+    match the oracle (Philox mode, ragged chunk sizes).  obs_format="nibbles" carries the same information in half
+    the PCIe bytes (4-bit cell codes, int16 reward and actions)."""
     import torch
-    n, moves = 3000, 6  # not a multiple of the chunk count or of the 32-board tile
+    n, moves = 3000 + (1 if obs_format == "nibbles" else 0), 6  # not a multiple of the chunk count or of the tile
     o = Oracle(9, 9, 6)
     a_env = E.BatchedMatch3Env(n, seed=11, num_moves=moves, env_goal=60)
     b_env = E.BatchedMatch3Env(n, seed=11, num_moves=moves, env_goal=60)
     boards = np_(a_env.init()).astype(np.int64)
     assert np.array_equal(boards, np_(b_env.init()))
-    hs = E.HostStepper(a_env, chunks=5)
+    hs = E.HostStepper(a_env, chunks=5, obs_format=obs_format)
+    small = torch.int16 if obs_format == "nibbles" else torch.int32
+    assert hs.d2h_bytes == n * ((41 + 2 + 2) if obs_format == "nibbles" else (81 + 4 + 2))
     score = np.zeros(n, dtype=np.int64)
     for t in range(moves):
         acts = hs.random_action()
-        assert acts.is_pinned() and acts.dtype == torch.int32
-        a = acts.numpy().copy()
+        assert acts.is_pinned() and acts.dtype == small
+        a = acts.numpy().astype(np.int32)
         obs, rew, done, won, _ = hs.step(acts)
         for x in (obs, rew, done, won):
             assert x.device.type == "cpu" and x.is_pinned()
-        assert done.dtype == torch.bool and won.dtype == torch.bool
+        assert done.dtype == torch.bool and won.dtype == torch.bool and rew.dtype == small
+        if obs_format == "nibbles":
+            assert obs.shape == (n, 41) and obs.dtype == torch.uint8
+            cells = hs.decode_obs(obs)
+        else:
+            cells = obs.numpy()
         obs2, rew2, done2, won2, _ = b_env.step(torch.from_numpy(a).to(b_env.board.device))
-        assert np.array_equal(obs.numpy(), np_(obs2)) and np.array_equal(rew.numpy(), np_(rew2))
+        assert np.array_equal(cells, np_(obs2)) and np.array_equal(rew.numpy(), np_(rew2))
         assert np.array_equal(done.numpy(), np_(done2)) and np.array_equal(won.numpy(), np_(won2))
         res = o.step_batch(boards, a, mode="philox", key=a_env.board.key, board0=0, step_ctr=t)
-        assert np.array_equal(obs.numpy(), res["boards"]) and np.array_equal(rew.numpy(), res["reward"])
+        assert np.array_equal(cells, res["boards"]) and np.array_equal(rew.numpy(), res["reward"])
         score += res["reward"]
         assert np.array_equal(won.numpy(), score >= 60)
         assert np.array_equal(done.numpy(), (score >= 60) | (t == moves - 1))
         boards = res["boards"]
+
+
+def test_nibble_observation_all_codes_and_shapes(E):
+    """ecg_unpack_nibbles: 4-bit cell codes, two per byte, ceil(R*C/2) bytes per board, ragged tiles, odd R*C"""
+    import ctypes as C
+    import torch
+    for shape in ((9, 9, 6), (5, 5, 2), (16, 16, 8), (6, 6, 4)):
+        o = Oracle(*shape)
+        rng = np.random.default_rng(4)
+        vals = np.array(list(range(0, shape[2] + 1)) + [o.cfg.h_line, o.cfg.v_line, o.cfg.bomb, o.cfg.mega_token])
+        codes = np.array(list(range(0, shape[2] + 1)) + [12, 13, 14, 15])
+        for n in (1, 31, 32, 33, 1001):
+            pick = rng.integers(len(vals), size=(n, shape[0], shape[1]))
+            bb = E.BatchedBoards(cfg_of(E, shape), n, arrays=vals[pick].astype(np.int64), key=KEY)
+            nby = (shape[0] * shape[1] + 1) // 2
+            buf = torch.full((n * nby + 64,), 0xAB, dtype=torch.uint8, device=bb.device)
+            N = E._native
+            N.check(N.lib().ecg_unpack_nibbles(C.byref(bb.nat), C.c_void_p(bb.boards.data_ptr()),
+                                               C.c_void_p(buf.data_ptr()), n, None), "ecg_unpack_nibbles")
+            torch.cuda.synchronize()
+            got = np_(buf[:n * nby]).reshape(n, nby)
+            flat = codes[pick].reshape(n, -1)
+            if flat.shape[1] % 2:
+                flat = np.concatenate([flat, np.zeros((n, 1), dtype=flat.dtype)], axis=1)
+            want = (flat[:, 0::2] | (flat[:, 1::2] << 4)).astype(np.uint8)
+            assert np.array_equal(got, want), (shape, n)
+            assert bool((buf[n * nby:] == 0xAB).all())
 
 
 def test_boardv2_view_matches_golden_and_state_abc(E):
@@ -430,6 +466,125 @@ def test_expand_and_greedy_vs_oracle(E):
     for j in range(0, len(par), 37):
         r1 = o.step_batch(boards[par[j]:par[j] + 1], act[j:j + 1], mode="philox", key=KEY, board0=50 + int(par[j]), step_ctr=3)
         assert np.array_equal(np_(ch.array[j:j + 1]), r1["boards"]) and int(ch.step_reward[j]) == r1["reward"][0]
+
+
+def oracle_pick(o, raw, pos, legal_row):
+    """np.random.choice(legal_actions) on the replayed stream at word `pos` -> (action, new position)"""
+    import ctypes as C
+    rng = o.rng_replay(raw)
+    rng.pos = int(pos)
+    la = np.flatnonzero(legal_row)
+    k = o.L.ecgo_rng_below(C.byref(rng), C.c_uint32(len(la)))
+    return int(la[k]), int(rng.pos)
+
+
+@pytest.mark.parametrize("shape", [(9, 9, 6), (6, 6, 4)])
+def test_shared_stream_replay_many_boards(E, shape):
+    """SURVEY 8d config 2 "variant": n > 1 boards that all replay ONE MT(cfg.seed) stream (stream_stride = 0) -- the
+    reference's situation for every state of one BoardConfig (MCTS leaves, greedy children).  Random picks continue
+    the stream behind each board's own refill draws.  Checked against the oracle and against the per-board-stream
+    layout (stride > 0) fed with n copies of the same seed."""
+    n, moves, seed = 777, 6, 4242
+    o = Oracle(*shape)
+    rng = np.random.default_rng(9)
+    # different boards, same seed: boards reached by Philox play from random starts
+    start = E.BatchedBoards(cfg_of(E, shape, seed), n, 3, key=KEY)
+    for _ in range(3):
+        start.apply_action(None)
+    boards = np_(start.array)
+    raw = Oracle.mt_raw(seed, 4096)
+    shared = E.BatchedBoards(cfg_of(E, shape, seed), n, moves, arrays=boards, refill="replay", seeds=[seed])
+    strided = E.BatchedBoards(cfg_of(E, shape, seed), n, moves, arrays=boards, refill="replay", seeds=[seed] * n)
+    assert shared.stream_stride == 0 and strided.stream_stride == 4096
+    assert shared.stream.numel() == 4096 and np.array_equal(np_(shared.stream).view(np.uint32), raw)
+    pos = np.zeros(n, dtype=np.int64)
+    for t in range(moves):
+        legal = o.legal_mask_batch(boards)
+        if t % 2 == 0:
+            acts = None  # fused pick inside the step kernel
+            want = [oracle_pick(o, raw, pos[i], legal[i])[0] for i in range(n)]
+        else:
+            acts = np_(shared.random_action())  # separate pick kernel (advances stream_pos; the step restarts it)
+            want = [oracle_pick(o, raw, pos[i], legal[i])[0] for i in range(n)]
+            assert acts.tolist() == want
+        shared.apply_action(acts)
+        strided.apply_action(acts)
+        a = np_(shared.last_actions)
+        assert a.tolist() == want and np.array_equal(a, np_(strided.last_actions))
+        res = o.step_batch(boards, a, mode="replay", raw=raw)
+        assert not res["status"].any() and not np_(shared.status).any()
+        for bb in (shared, strided):
+            assert np.array_equal(np_(bb.array), res["boards"])
+            assert np.array_equal(np_(bb.step_reward), res["reward"])
+            assert np.array_equal(np_(bb.cascades), res["cascades"])
+            assert np.array_equal(np_(bb.legal_mask()), res["legal"])
+        assert np.array_equal(np_(shared.stream_pos), np_(strided.stream_pos))
+        pos = np_(shared.stream_pos).astype(np.int64)
+        boards = res["boards"]
+    # the same boards in ONE rollout kernel
+    roll = E.BatchedBoards(cfg_of(E, shape, seed), n, moves, arrays=np_(start.array), refill="replay", seeds=[seed])
+    total = roll.rollout()
+    assert np.array_equal(np_(total), np_(shared.reward)) and np.array_equal(np_(roll.array), boards)
+
+
+def test_replay_children_keep_their_parents_streams(E):
+    """expand() in replay mode with one stream per board: child j replays the stream of ITS parent (stream_index)
+    from the position its own step reached -- checked by stepping the children (random pick + explicit action) and
+    the grandchildren against the oracle."""
+    shape = (9, 9, 6)
+    o = Oracle(*shape)
+    n = 41
+    seeds = np.arange(500, 500 + n, dtype=np.int64)
+    raw = np.stack([Oracle.mt_raw(int(s), 2048) for s in seeds])
+    bb = E.BatchedBoards(cfg_of(E, shape), n, 6, refill="replay", seeds=seeds, stream_len=2048)
+    boards = np_(bb.array)
+    child, parent, action = bb.expand()
+    parent, action = np_(parent), np_(action)
+    p = len(parent)
+    assert p > 8 * n and np.array_equal(np_(child.stream_index), parent)
+    res = o.step_batch(boards[parent], action, mode="replay", raw=raw[parent])
+    assert np.array_equal(np_(child.array), res["boards"])
+    # stream_pos of a child = words its step drew
+    pos = np_(child.stream_pos)
+    want_pick = [oracle_pick(o, raw[parent[j]], pos[j], res["legal"][j])[0] for j in range(p)]
+    c2 = child.clone()
+    assert c2.stream_index is child.stream_index
+    c2.apply_action(None)  # np.random.choice continuing the parent's stream
+    assert np_(c2.last_actions).tolist() == want_pick
+    res2 = o.step_batch(res["boards"], np.array(want_pick), mode="replay", raw=raw[parent])
+    assert np.array_equal(np_(c2.array), res2["boards"]) and np.array_equal(np_(c2.step_reward), res2["reward"])
+    assert np.array_equal(np_(c2.reward), res["reward"] + res2["reward"])
+    # grandchildren: stream_index composes
+    g, gpar, gact = child.expand()
+    gpar, gact = np_(gpar), np_(gact)
+    assert np.array_equal(np_(g.stream_index), parent[gpar])
+    sel = np.arange(0, len(gpar), 53)
+    res3 = o.step_batch(res["boards"][gpar[sel]], gact[sel], mode="replay", raw=raw[parent[gpar[sel]]])
+    assert np.array_equal(np_(g.array)[sel], res3["boards"]) and np.array_equal(np_(g.step_reward)[sel], res3["reward"])
+    # whole-episode rollout of the children on their parents' streams == stepping them with random picks
+    r = child.clone()
+    tot = r.rollout()
+    s = child.clone()
+    for _ in range(5):
+        s.apply_action(None)
+    assert np.array_equal(np_(tot) + res["reward"], np_(s.reward)) and np.array_equal(np_(r.array), np_(s.array))
+
+
+def test_unpack_uint8_partial_tiles_stay_in_bounds(E):
+    """uint8 observations are written 4 cells per store: the last word of a partial tile must not run past the
+    n*R*C cells that exist (81 cells for n = 1 on 9x9: round-1 advisor finding)."""
+    import torch
+    for shape in ((9, 9, 6), (5, 5, 2), (7, 7, 5), (6, 6, 4)):
+        for n in (1, 2, 3, 33, 35):
+            o = Oracle(*shape)
+            bb = E.BatchedBoards(cfg_of(E, shape), n, key=KEY)
+            want = np_(bb.array).astype(np.uint8)
+            cells = n * shape[0] * shape[1]
+            buf = torch.full((cells + 64,), 0xAB, dtype=torch.uint8, device=bb.device)
+            out = buf[:cells].view(n, shape[0], shape[1])
+            bb.observe(torch.uint8, out=out)
+            assert np.array_equal(np_(out), want)
+            assert bool((buf[cells:] == 0xAB).all()), (shape, n)
 
 
 def test_onehot_observation(E):
