@@ -988,11 +988,11 @@ ECG_PHASE void gravity(Board<G> &b) {
     for (;;) {
         const BB<W> occ = b.p[0] | b.p[1] | b.p[2] | b.p[3];
         const BB<W> holes = andn(G::valid(), occ);
-        BB<W> u = shr<S>(holes); // a hole somewhere below in the column
-        u |= shr<S>(u);
-        u |= shr<2 * S>(u);
-        if (G::R > 4) u |= shr<4 * S>(u);
-        if (G::R > 8) u |= shr<8 * S>(u);
+        BB<W> u = shr<S>(holes); // a hole 1 row below ...
+        u |= shr<S>(u);          // ... 1..2 rows below
+        u |= shr<2 * S>(u);      // ... 1..4
+        if (G::R > 5) u |= shr<4 * S>(u); // ... 1..8 (the bottom row is R - 1 rows below the top one)
+        if (G::R > 9) u |= shr<8 * S>(u); // ... 1..16
         const BB<W> f = occ & u;
         if (!any(f)) return;
 #pragma unroll
@@ -1240,44 +1240,38 @@ ECG_HD bool step_begin_at(Lane<SH> &L, int b1, int d) {
     L.cascades = 0;
     L.status = 0;
     const int b2 = b1 + d;
-    int c1 = 0, c2 = 0; // cell codes of source / target AFTER the swap
-    { // swap (:51): both cells sit in the 64-bit window that starts at the word of b1
-        const int wi = b1 >> 5, s = b1 & 31;
-        const BB<W> both = onehot<W>(b1) | onehot<W>(b2);
-        uint32_t sel[W]; // all-ones for the word of b1 (AND/OR masks: a select chain over w[] would be turned into
-#pragma unroll           // a dynamically indexed local-memory array by the compiler)
-        for (int i = 0; i < W; i++) sel[i] = (i == wi) ? 0xFFFFFFFFu : 0u;
+    // swap (:51).  Per plane the two cells' bits are gathered into one word (they sit at different bit positions
+    // modulo 32, because d is 1 or S < 32): the plane changes iff exactly one of them is set.
+    const BB<W> m1 = onehot<W>(b1), m2 = onehot<W>(b2);
+    const BB<W> both = m1 | m2;
+    uint32_t pair = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t lo = 0, hi = 0;
+    for (int i = 0; i < W; i++) pair |= both.w[i];
 #pragma unroll
-            for (int i = 0; i < W; i++) {
-                lo |= bd.p[k].w[i] & sel[i];
-                if (i > 0) hi |= bd.p[k].w[i] & sel[i - 1];
-            }
-            const uint32_t x = funnel_r(lo, hi, s);
-            const uint32_t v1 = x & 1u, v2 = (x >> d) & 1u; // old bits of source / target
-            c1 |= (int)(v2 << k);
-            c2 |= (int)(v1 << k);
-            const uint32_t flip = 0u - (v1 ^ v2);
+    for (int k = 0; k < 4; k++) {
+        uint32_t x = 0;
 #pragma unroll
-            for (int i = 0; i < W; i++) bd.p[k].w[i] ^= both.w[i] & flip;
-        }
+        for (int i = 0; i < W; i++) x |= bd.p[k].w[i] & both.w[i];
+        const uint32_t flip = (x != 0u && x != pair) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+        for (int i = 0; i < W; i++) bd.p[k].w[i] ^= both.w[i] & flip;
     }
-    const int s1 = c1 >= 12 ? c1 - 11 : 0, s2 = c2 >= 12 ? c2 - 11 : 0; // 0 none, 1 h, 2 v, 3 bomb, 4 mega
     bool matched = true;
     L.sp = bb_zero<W>();
     L.sk0 = bb_zero<W>();
     L.sk1 = bb_zero<W>();
     L.cleared = bb_zero<W>();
-    if (s1 | s2) {
+    const BB<W> spec2 = bd.p[3] & bd.p[2] & both;
+    if (any(spec2)) { // a special token was moved
         if constexpr (FAST) {
             // one special + a plain token (1.9 % of random legal steps: a typeless special makes every swap with
             // it legal) is special_pair_impl's last line: get_matches decides -- except mega + plain, which clears
             // nothing (:84-103).  Two specials go to the exact build.
-            if (s1 && s2) return true;
-            matched = (s1 | s2) != 4;
+            if (any(spec2 & m1) && any(spec2 & m2)) return true;
+            matched = !any(bd.p[0] & bd.p[1] & spec2); // code 15 = mega
         } else {
+            const int c1 = cell_code<G>(bd, b1), c2 = cell_code<G>(bd, b2); // source / target AFTER the swap
+            const int s1 = c1 >= 12 ? c1 - 11 : 0, s2 = c2 >= 12 ? c2 - 11 : 0; // 0 none, 1 h, 2 v, 3 bomb, 4 mega
             const PairOut<G> o = special_pair<G>(s1, s2, b2);
             L.cleared = o.cleared;
             matched = o.matched;
