@@ -113,21 +113,48 @@ RefillDev to_dev(const ecg_refill *rf) {
     return d;
 }
 
+// -DECG_ONLY_SIZE=N: a one-size experiment build (scripts/build_variant.sh)
 const ShapeOps *ops_for(int rows) {
     switch (rows) {
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 4
     case 4: return shape_ops_4();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 5
     case 5: return shape_ops_5();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 6
     case 6: return shape_ops_6();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 7
     case 7: return shape_ops_7();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 8
     case 8: return shape_ops_8();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 9
     case 9: return shape_ops_9();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 10
     case 10: return shape_ops_10();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 11
     case 11: return shape_ops_11();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 12
     case 12: return shape_ops_12();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 13
     case 13: return shape_ops_13();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 14
     case 14: return shape_ops_14();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 15
     case 15: return shape_ops_15();
+#endif
+#if !defined(ECG_ONLY_SIZE) || ECG_ONLY_SIZE == 16
     case 16: return shape_ops_16();
+#endif
     default: return nullptr;
     }
 }
