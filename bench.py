@@ -382,8 +382,10 @@ def run_ours(args):
             del rb
             torch.cuda.empty_cache()
         del src
-        replay["kernel"] = ("lane_kernel<Shape<9,9,3,false>, replay, step, exact> (one launch per step: the exact build, "
-                            "refill tiles and picks by numpy's masked rejection over the raw MT19937 words in HBM)")
+        replay["kernel"] = ("two-kernel replay step: lane_kernel<Shape<9,9,3,false>, replay, step, FAST> reads its refill "
+                            "tiles from per-stream tile tables (ecg_replay_tiles: the accepted values of numpy's masked "
+                            "rejection over the raw MT19937 words, 16 per window), picks by masked rejection on the raw "
+                            "words; rare cases go to lane_kernel<..., replay, step, exact>")
         replay["philox_for_comparison"] = {"mean_cascades_per_step": mean_casc, "mean_reward_per_step": mean_reward}
 
     cpu = None

@@ -32,7 +32,7 @@ class Refill(C.Structure):
     _fields_ = [("mode", C.c_int32), ("stream_len", C.c_int32), ("stream", C.c_void_p),
                 ("stream_stride", C.c_int64), ("stream_pos", C.c_void_p), ("philox_key", C.c_uint64),
                 ("board0", C.c_uint64), ("step_ctr", C.c_uint32), ("reserved", C.c_uint32),
-                ("stream_index", C.c_void_p)]
+                ("stream_index", C.c_void_p), ("tiles", C.c_void_p), ("tile_wpos", C.c_void_p)]
 
 
 class StepIO(C.Structure):
@@ -59,6 +59,8 @@ EXPORTS = {
     "ecg_unpack_nibbles": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_unpack_mask": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_mt19937_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "ecg_replay_tiles_words": (C.c_int64, [C.c_int32]),
+    "ecg_replay_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_init_boards": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_legal_mask": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_random_action": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_void_p,

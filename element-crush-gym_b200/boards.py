@@ -56,6 +56,7 @@ class BatchedBoards:
         self.stream = None
         self.stream_pos = None
         self.stream_index = None  # replay: int32 [n], board i replays stream stream_index[i] (children of expand())
+        self.tiles = self.tile_wpos = None  # replay: per-stream tile tables (ecg_replay_tiles) of the two-kernel step
         self.stream_len = 0
         self.stream_stride = 0
         self._moves_bound = max(int(n_actions), 0)  # host-side upper bound of moves_left (no device read needed)
@@ -72,8 +73,9 @@ class BatchedBoards:
         self.flags = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.status = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.last_actions = torch.full((self.n,), -1, dtype=torch.int32, device=dev)
-        # work list of the two-kernel Philox step (ecg_step_io.scratch); ECG_SINGLE_KERNEL=1 keeps the one-kernel step
-        self.two_kernel_step = refill == "philox" and os.environ.get("ECG_SINGLE_KERNEL", "0") != "1"
+        # work list of the two-kernel step (ecg_step_io.scratch); ECG_SINGLE_KERNEL=1 keeps the one-kernel step
+        self.two_kernel_step = (os.environ.get("ECG_SINGLE_KERNEL", "0") != "1" and
+                                (refill == "philox" or stream_len < 65535))
         self._scratch = torch.empty(self.n + 1, dtype=torch.int32, device=dev) if self.two_kernel_step else None
         if _empty:
             return
@@ -94,6 +96,8 @@ class BatchedBoards:
             N.check(self.L.ecg_mt19937_stream(_ptr(sd), _ptr(self.stream), self.stream_len, sd.numel(), _stream(dev)),
                     "ecg_mt19937_stream")
             self.stream_stride = self.stream_len if (sd.numel() == self.n and self.n > 1) or stream_index is not None else 0
+            if self.two_kernel_step:
+                self._build_tiles(sd.numel())
             self.stream_pos = torch.zeros(self.n, dtype=torch.int32, device=dev)
         elif refill != "philox":
             raise ValueError("refill must be 'philox' or 'replay'")
@@ -105,6 +109,16 @@ class BatchedBoards:
                                            self.n, _stream(dev)), "ecg_init_boards")
 
     # ------------------------------------------------------------------ plumbing
+    def _build_tiles(self, n_streams: int):
+        """tile tables of the replay streams for this config's `types` (the two-kernel replay step reads its refill
+        tiles from them instead of rejection-sampling raw words)"""
+        dev = self.device
+        tw = int(self.L.ecg_replay_tiles_words(self.stream_len))
+        self.tiles = torch.empty(n_streams * tw, dtype=torch.int32, device=dev)
+        self.tile_wpos = torch.empty(n_streams * (self.stream_len + 1), dtype=torch.int16, device=dev)
+        N.check(self.L.ecg_replay_tiles(_ptr(self.stream), self.stream_len, self.cfg.types, _ptr(self.tiles),
+                                        _ptr(self.tile_wpos), n_streams, _stream(dev)), "ecg_replay_tiles")
+
     def _refill(self, step_ctr=None) -> N.Refill:
         rf = N.Refill()
         if self.refill_mode == "philox":
@@ -120,6 +134,9 @@ class BatchedBoards:
             rf.stream_pos = self.stream_pos.data_ptr()
             if self.stream_index is not None:
                 rf.stream_index = self.stream_index.data_ptr()
+            if self.tiles is not None and self.two_kernel_step:
+                rf.tiles = self.tiles.data_ptr()
+                rf.tile_wpos = self.tile_wpos.data_ptr()
         return rf
 
     def set_arrays(self, arrays):
@@ -261,6 +278,7 @@ class BatchedBoards:
         c.step_ctr = self.step_ctr
         c.stream, c.stream_len, c.stream_stride = self.stream, self.stream_len, self.stream_stride  # read-only, shared
         c.stream_index = self.stream_index  # read-only, shared
+        c.tiles, c.tile_wpos = self.tiles, self.tile_wpos
         c.stream_pos = None if self.stream_pos is None else self.stream_pos.clone()
         c._moves_bound = self._moves_bound
         return c
@@ -280,6 +298,7 @@ class BatchedBoards:
         child = BatchedBoards(self.cfg, p, device=self.device, refill=self.refill_mode, key=self.key,
                               board0=self.board0, env_goal=self.env_goal, _empty=True)
         child.stream, child.stream_len, child.stream_stride = self.stream, self.stream_len, self.stream_stride
+        child.tiles, child.tile_wpos = self.tiles, self.tile_wpos
         child.step_ctr = self.step_ctr + 1
         child._moves_bound = max(self._moves_bound - 1, 0)
         src = parent.to(torch.int32).contiguous()

@@ -67,6 +67,15 @@ __global__ void __launch_bounds__(64) mt19937_kernel(const uint32_t *__restrict_
     }
 }
 
+// per-stream tile tables of the replay two-kernel step (ecg_core.cuh build_replay_tiles): one thread per stream
+__global__ void __launch_bounds__(64) replay_tiles_kernel(const uint32_t *__restrict__ raw, int len, int types,
+                                                          uint32_t *__restrict__ tiles, uint16_t *__restrict__ wpos,
+                                                          long long n) {
+    const long long i = (long long)blockIdx.x * 64 + threadIdx.x;
+    if (i >= n) return;
+    build_replay_tiles(raw + i * len, len, (uint32_t)types, tiles + i * replay_tile_words(len), wpos + i * (len + 1));
+}
+
 __global__ void __launch_bounds__(256) stats_kernel(const int32_t *__restrict__ score, const uint8_t *__restrict__ flags,
                                                     long long *out, long long n) {
     long long sum = 0, sq = 0, cnt = 0, wins = 0, mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
@@ -110,6 +119,8 @@ RefillDev to_dev(const ecg_refill *rf) {
     d.step_ctr = rf->step_ctr;
     d.stream_len = rf->stream_len;
     d.stream_index = rf->stream_index;
+    d.tiles = rf->tiles;
+    d.tile_wpos = rf->tile_wpos;
     return d;
 }
 
@@ -172,6 +183,10 @@ int check_refill(const ecg_refill *rf) {
     if (rf->mode == ECG_REFILL_REPLAY) {
         if (!rf->stream || rf->stream_len <= 0 || rf->stream_stride < 0)
             return fail("replay refill needs stream, stream_len > 0, stream_stride >= 0");
+        if ((rf->tiles != nullptr) != (rf->tile_wpos != nullptr) || (rf->tiles && rf->stream_len >= (int32_t)REPLAY_TILES_END))
+            return fail("replay refill: tiles and tile_wpos come together (ecg_replay_tiles, stream_len < 65535)");
+        if (rf->tiles && rf->stream_stride != 0 && rf->stream_stride != rf->stream_len)
+            return fail("replay refill: tile tables need stream_stride == 0 or == stream_len");
         return 0;
     }
     return fail("refill mode must be ECG_REFILL_REPLAY or ECG_REFILL_PHILOX");
@@ -267,6 +282,20 @@ int ecg_mt19937_stream(const uint32_t *seeds, uint32_t *out, int32_t len, int64_
     if (n <= 0) return 0;
     mt19937_kernel<<<grid_for(n, 64), 64, 0, (cudaStream_t)stream>>>(seeds, out, len, n);
     return check_launch("ecg_mt19937_stream");
+}
+
+int64_t ecg_replay_tiles_words(int32_t stream_len) { return stream_len > 0 ? replay_tile_words(stream_len) : 0; }
+
+int ecg_replay_tiles(const uint32_t *streams, int32_t stream_len, int types, uint32_t *tiles, uint16_t *tile_wpos,
+                     int64_t n_streams, void *stream) {
+    if (!streams || !tiles || !tile_wpos) return fail("ecg_replay_tiles: NULL buffer");
+    if (stream_len <= 0 || stream_len >= (int32_t)REPLAY_TILES_END)
+        return fail("ecg_replay_tiles: stream_len must be in 1..65534 (16-bit word positions)");
+    if (types < 1 || types > 11) return fail("ecg_replay_tiles: types must be in 1..11");
+    if (n_streams <= 0) return 0;
+    replay_tiles_kernel<<<grid_for(n_streams, 64), 64, 0, (cudaStream_t)stream>>>(streams, stream_len, types, tiles,
+                                                                                  tile_wpos, n_streams);
+    return check_launch("ecg_replay_tiles");
 }
 
 int ecg_init_boards(const ecg_config *cfg, const ecg_refill *rf, void *boards, uint8_t *status, int64_t n,

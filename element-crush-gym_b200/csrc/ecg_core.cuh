@@ -29,6 +29,14 @@ constexpr int CASCADE_CAP = 1024;
 
 enum : int { K_HLINE = 0, K_VLINE = 1, K_BOMB = 2, K_MEGA = 3 };
 
+// host experiments only (-DECG_COUNT_RARE): why the common-case build hands boards off
+#if defined(ECG_COUNT_RARE) && !defined(__CUDA_ARCH__)
+extern long long g_rare_reason[8];
+#define ECG_RARE(i) (g_rare_reason[i]++)
+#else
+#define ECG_RARE(i) ((void)0)
+#endif
+
 // ------------------------------------------------------------------ RNG sources
 
 // Philox4x32-10 (Salmon et al. SC'11).  One substream per (board, step):
@@ -235,6 +243,81 @@ struct ReplayRng {
         }
     }
     ECG_HD uint32_t digit(uint32_t n) { return below(n); } // np.random.randint(1, types + 1) per tile
+};
+
+// Replay mode, common-case kernel.  Within one apply_action the refill tiles are a PREFIX of the stream's
+// accepted-tile sequence: np.random.randint(1, types + 1) is masked rejection with one fixed mask over the raw words,
+// restarted by np.random.seed(cfg.seed) at the top of the step (boardv2.py:46, :172) -- until a shuffle draws with
+// another bound (boardFunctions.py:22), which the common-case build hands to the exact build anyway.  So the tiles
+// are precomputed once per stream: tile j as a nibble (1..types, 8 per word, first tile in the low nibble) and
+// wpos[j] = raw words consumed once j tiles are taken (REPLAY_TILES_END past the end of the stream); the refill then
+// reads 16 tiles per window like the Philox path instead of one raw word per rejection round.
+constexpr uint32_t REPLAY_TILES_END = 0xFFFFu;
+ECG_HD_CONSTEXPR int replay_tile_words(int stream_len) { return (stream_len + 7) / 8 + 2; } // + 2: window over-read
+ECG_HD void build_replay_tiles(const uint32_t *raw, int len, uint32_t types, uint32_t *tiles, uint16_t *wpos) {
+    const int tw = replay_tile_words(len);
+    for (int i = 0; i < tw; i++) tiles[i] = 0u;
+    const uint32_t rng = types - 1u;
+    uint32_t mask = rng;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    int j = 0;
+    wpos[0] = 0;
+    if (rng == 0u) { // randint(1, 2): no word is drawn
+        for (j = 1; j <= len; j++) {
+            tiles[(j - 1) >> 3] |= 1u << (4 * ((j - 1) & 7));
+            wpos[j] = 0;
+        }
+        return;
+    }
+    for (int k = 0; k < len; k++) {
+        const uint32_t v = raw[k] & mask;
+        if (v <= rng) {
+            tiles[j >> 3] |= (v + 1u) << (4 * (j & 7));
+            wpos[++j] = (uint16_t)(k + 1);
+        }
+    }
+    for (int t = j + 1; t <= len; t++) wpos[t] = (uint16_t)REPLAY_TILES_END;
+}
+
+struct ReplayTileRng {
+    static constexpr bool ROW_MAJOR = false; // the reference's order: columns left to right, top cell first
+    static constexpr bool TILE_WINDOW = true;
+    const uint32_t *tiles;
+    const uint16_t *wpos;
+    uint32_t tpos; // tiles taken since the last reseed
+    bool overflow;
+    ECG_HD void init(const uint32_t *tiles_, const uint16_t *wpos_, uint32_t tpos_) {
+        tiles = tiles_;
+        wpos = wpos_;
+        tpos = tpos_;
+        overflow = false;
+    }
+    ECG_HD void reseed() { tpos = 0; }
+    ECG_HD void seek(uint32_t) {}
+    // the 16 tiles from tile t on, one per nibble, first in the low nibble of lo; past the end of the stream the
+    // window is filled with dummies and overflow is set (the caller drops the board)
+    ECG_HD void window(uint32_t t, uint32_t &lo, uint32_t &hi) {
+        const uint32_t *p = tiles + (t >> 3);
+        const int sh = (int)(t & 7u) * 4;
+        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+        lo = funnel_r(w0, w1, sh);
+        hi = funnel_r(w1, w2, sh);
+        if ((lo & 15u) == 0u) {
+            overflow = true;
+            lo = hi = 0x11111111u;
+        }
+    }
+    ECG_HD uint32_t words() const { return wpos[tpos]; } // raw words behind the tiles taken (np.random's position)
+};
+template <class RNG>
+struct UsesTileWindow {
+    static constexpr bool value = false;
+};
+template <>
+struct UsesTileWindow<ReplayTileRng> {
+    static constexpr bool value = true;
 };
 
 // ------------------------------------------------------------------ board
@@ -679,6 +762,14 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
             //   neither (merged T / + shape)            : everything cleared, bomb on x -- or on the cell left
             //                                             of x when x is the bottom of V and the right end of H
             if (popcount(X) != 1 || any(L4h | L4v)) {
+                ECG_RARE(popcount(X) != 1 ? 0 : 1);
+#if defined(ECG_COUNT_RARE) && !defined(__CUDA_ARCH__)
+                if (popcount(X) == 1) {
+                    const BB<W> h4 = hs & shr<1>(hs), v4 = vs & shr<S>(vs);
+                    const BB<W> c4 = h4 | shl<1>(h4) | shl<2>(h4) | shl<3>(h4) | v4 | shl<S>(v4) | shl<2 * S>(v4) | shl<3 * S>(v4);
+                    ECG_RARE(any(X & c4) ? 5 : 6);
+                }
+#endif
                 m.rare = true;
                 m.mask = bb_zero<W>();
                 return;
@@ -711,6 +802,7 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
             add_spawn_disjoint<SH>(m, shl<2>(andn(L5h, L6h)) | shl<2 * S>(andn(L5v, L6v)), K_MEGA);
             if (any(L6h | L6v)) {
                 if constexpr (FAST) {
+                    ECG_RARE(2);
                     m.rare = true;
                     return;
                 }
@@ -1110,6 +1202,33 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
             }
         }
 #endif
+    } else if constexpr (UsesTileWindow<RNG>::value) {
+        // the reference's order with precomputed tiles (ReplayTileRng): 16 tiles per window, one nibble per hole
+        uint32_t t = rng.tpos, lo, hi;
+        uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
+        if (cols) rng.window(t, lo, hi);
+        while (cols) {
+            int bit = ctz32(cols);
+            cols &= cols - 1u;
+            do {
+                if (lo == 0u) rng.window(t, lo, hi); // 16 tiles used up (or the stream: dummies + overflow)
+                const int wi = bit >> 5;
+                const uint32_t m = 1u << (bit & 31);
+#pragma unroll
+                for (int i = 0; i < G::W; i++) {
+                    const uint32_t mi = (i == wi) ? m : 0u;
+                    deposit_bit<1>(b.p[0].w[i], lo, mi);
+                    deposit_bit<2>(b.p[1].w[i], lo, mi);
+                    deposit_bit<4>(b.p[2].w[i], lo, mi);
+                    if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[i], lo, mi);
+                }
+                lo = funnel_r(lo, hi, 4);
+                hi >>= 4;
+                t++;
+                bit += G::S;
+            } while (bit < G::NB && testbit(holes, bit));
+        }
+        rng.tpos = t;
     } else {
         uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
         while (cols) {
@@ -1267,7 +1386,10 @@ ECG_HD bool step_begin_at(Lane<SH> &L, int b1, int d) {
             // one special + a plain token (1.9 % of random legal steps: a typeless special makes every swap with
             // it legal) is special_pair_impl's last line: get_matches decides -- except mega + plain, which clears
             // nothing (:84-103).  Two specials go to the exact build.
-            if (any(spec2 & m1) && any(spec2 & m2)) return true;
+            if (any(spec2 & m1) && any(spec2 & m2)) {
+                ECG_RARE(3);
+                return true;
+            }
             matched = !any(bd.p[0] & bd.p[1] & spec2); // code 15 = mega
         } else {
             const int c1 = cell_code<G>(bd, b1), c2 = cell_code<G>(bd, b2); // source / target AFTER the swap
@@ -1324,6 +1446,10 @@ ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, B
     }
     gravity<G>(bd);                             // :166-170
     refill<SH>(bd, rng, types, L.cascades - 1); // :172-173
+    if (FAST && rng.overflow) { // replay stream exhausted: the exact build reports it
+        rare = true;
+        return false;
+    }
     Derived<G> d = derive<SH>(bd);
     Matches<G> m;
     find_matches<SH, FAST>(d, m); // :181
@@ -1335,6 +1461,7 @@ ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, B
     if (!m.found) {
         legal_swaps<SH>(d, m.A, m.D, HL, VL);
         if (FAST && !any(HL | VL)) {
+            ECG_RARE(4);
             rare = true;
             return false;
         }
@@ -1397,20 +1524,20 @@ ECG_HD void step_board(Board<typename SH::G> &bd, int action, uint32_t types, RN
 
 // The two-kernel step on one board: the common-case build first, the exact build from the unchanged input when it
 // hands the board off.  Host tests use it to fuzz the FAST logic against the oracle; returns true on a hand-off.
-template <class SH, class RNG>
-ECG_HD bool step_board_two_pass(Board<typename SH::G> &bd, int action, uint32_t types, RNG &rng, StepOut &out,
-                                BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
-    const RNG rng0 = rng;
+// frng drives the common-case pass, rng the exact pass (replay: ReplayTileRng / ReplayRng over the same stream); when
+// no board is handed off, rng is left untouched and frng holds the position.
+template <class SH, class FRNG, class RNG>
+ECG_HD bool step_board_two_pass(Board<typename SH::G> &bd, int action, uint32_t types, FRNG &frng, RNG &rng,
+                                StepOut &out, BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
     Lane<SH> L;
     L.bd = bd;
-    rng.reseed();
+    frng.reseed();
     int b1, b2;
     decode_action<typename SH::G>(action, b1, b2);
     bool rare = step_begin_at<SH, true>(L, b1, b2 - b1);
-    while (!rare && !step_iter<SH, RNG, true>(L, rng, types, HL, VL, rare)) {
+    while (!rare && !step_iter<SH, FRNG, true>(L, frng, types, HL, VL, rare)) {
     }
     if (rare) {
-        rng = rng0;
         step_board<SH>(bd, action, types, rng, out, HL, VL);
         return true;
     }
@@ -1419,6 +1546,14 @@ ECG_HD bool step_board_two_pass(Board<typename SH::G> &bd, int action, uint32_t 
     out.cascades = L.cascades;
     out.status = L.status;
     return false;
+}
+template <class SH, class RNG>
+ECG_HD bool step_board_two_pass(Board<typename SH::G> &bd, int action, uint32_t types, RNG &rng, StepOut &out,
+                                BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
+    RNG frng = rng;
+    const bool handed_off = step_board_two_pass<SH, RNG, RNG>(bd, action, types, frng, rng, out, HL, VL);
+    if (!handed_off) rng = frng;
+    return handed_off;
 }
 
 // BoardV2.__init__ (boardv2.py:20-27): draw a board, redraw matched cells until clean.

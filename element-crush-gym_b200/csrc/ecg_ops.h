@@ -14,6 +14,8 @@ struct RefillDev {
     uint32_t step_ctr;
     int stream_len;
     const int32_t *stream_index; // replay, optional: board i replays stream stream_index[i]
+    const uint32_t *tiles;       // replay, optional: per-stream tile tables (ecg_replay_tiles) -> two-kernel replay step
+    const uint16_t *tile_wpos;
 };
 
 struct StepDev {

@@ -104,6 +104,10 @@ __device__ __forceinline__ const uint32_t *stream_of(const RefillDev &rf, long l
     return rf.stream + (rf.stream_index ? (long long)rf.stream_index[i] : i) * rf.stream_stride;
 }
 
+__device__ __forceinline__ long long stream_id(const RefillDev &rf, long long i) {
+    return rf.stream_stride ? (rf.stream_index ? (long long)rf.stream_index[i] : i) : 0;
+}
+
 template <class SH>
 __device__ __forceinline__ void legal_of(const Board<typename SH::G> &b, BB<SH::G::W> &HL, BB<SH::G::W> &VL) {
     using G = typename SH::G;
@@ -324,15 +328,17 @@ __global__ void __launch_bounds__(BLOCK) legal_kernel(const void *boards, uint32
 }
 
 
-template <bool PHILOX>
-struct RngOf;
-template <>
-struct RngOf<true> {
+template <bool PHILOX, bool FAST = false>
+struct RngOf {
     using type = PhiloxRng;
 };
 template <>
-struct RngOf<false> {
+struct RngOf<false, false> {
     using type = ReplayRng;
+};
+template <>
+struct RngOf<false, true> { // the common-case kernel of a replay step reads the precomputed tile tables
+    using type = ReplayTileRng;
 };
 
 template <class SH, bool PHILOX>
@@ -398,6 +404,12 @@ constexpr int CHUNK_BOARDS = ECG_CHUNK;
 // free-running warps each streamed it on their own (stall_no_inst 56 % of stall samples, GPC instruction-fetch path
 // at 96 % of peak).  In lockstep a cache line fetched by one warp is reused by the other 15: +11 % env-steps/s
 // (4.39e9 -> 4.87e9 at 9x9x6; 128 x 4 in lockstep: 4.40e9, 256 x 2: 4.84e9, 512 x 1: 4.87e9).
+// Boards of 16x16 (9 words per plane) need ~250 registers: 512-thread blocks (128 registers) spilled 650 B per thread
+// (r04b: 1.42e9 env-steps/s; 256 threads x 255 registers: 1.98e9; 384 x 168: 1.67e9).  12x12 is best at 512.
+#if ECG_SIZE >= 16 && !defined(ECG_LANE_BLOCK) && !defined(ECG_FAST_BLOCK)
+#define ECG_LANE_BLOCK 256
+#define ECG_FAST_BLOCK 256
+#endif
 #ifndef ECG_LANE_BLOCK
 #define ECG_LANE_BLOCK 512
 #endif
@@ -647,7 +659,11 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
             }
         }
         if constexpr (FAST) { // a board dropped in this trip is still to be appended to the hand-off list below
+#if defined(ECG_FAST_LOCKSTEP) // measured alternative for the largest boards, whose unrolled body outgrows the i-cache
+            if (!__syncthreads_or(state != IDLE || handoff)) break;
+#else
             if (!__any_sync(FULL, state != IDLE || handoff)) break;
+#endif
         } else {
             if (!ROLLOUT && io.n_jobs) { // the short job list of a two-kernel step: too few trips to pay for barriers
                 if (!__any_sync(FULL, state != IDLE)) break;
@@ -655,15 +671,21 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
         }
         // ---- ITERATE: one cascade iteration on every active lane; FINISH the steps whose cascade ended
         if (state == ACTIVE) {
-            typename RngOf<PHILOX>::type rng;
+            typename RngOf<PHILOX, FAST>::type rng;
             if constexpr (PHILOX) {
                 rng.init(rf.key, rf.board0 + (unsigned long long)src, step);
                 rng.preset_block(blk_index, blk);
+            } else if constexpr (FAST) { // rpos counts TILES while the step is in flight (converted at the end)
+                const long long sid = stream_id(rf, src);
+                rng.init(rf.tiles + sid * replay_tile_words(rf.stream_len), rf.tile_wpos + sid * (rf.stream_len + 1), rpos);
             } else {
                 rng.init(stream_of(rf, src), (uint32_t)rf.stream_len, rpos);
             }
-            const bool fin = step_iter<SH, typename RngOf<PHILOX>::type, FAST>(L, rng, (uint32_t)types, HL, VL, handoff);
-            if constexpr (!PHILOX) rpos = rng.pos;
+            const bool fin = step_iter<SH, typename RngOf<PHILOX, FAST>::type, FAST>(L, rng, (uint32_t)types, HL, VL, handoff);
+            if constexpr (!PHILOX) {
+                if constexpr (FAST) rpos = fin ? rng.words() : rng.tpos; // np.random's position once the step is over
+                else rpos = rng.pos;
+            }
             if (FAST && handoff) state = IDLE;
             if (fin) {
                 if constexpr (ROLLOUT) {
@@ -775,26 +797,32 @@ void launch_lanes(RefillDev rf, StepDev io, RolloutDev ro, int types, long long 
         <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT, FAST>, n, B), B, 0, s>>>(rf, io, ro, types, (int)n);
 }
 
-// Philox mode with a hand-off list: the common-case kernel over all boards, then the exact kernel over the jobs it
-// handed off (their number is read on the device: no host synchronisation in between)
-template <class SH>
+// The two-kernel step (Philox mode, or replay mode with tile tables): the common-case kernel over all boards, then the
+// exact kernel over the jobs it handed off (their number is read on the device: no host synchronisation in between)
+template <class SH, bool PHILOX>
 void launch_two_kernel_step(RefillDev rf, StepDev io, long long n, cudaStream_t s) {
     const RolloutDev ro = {};
     cudaMemsetAsync(io.handoff, 0, sizeof(int32_t), s);
-    launch_lanes<SH, true, false, true>(rf, io, ro, io.types, n, s);
+    launch_lanes<SH, PHILOX, false, true>(rf, io, ro, io.types, n, s);
     if (io.mid_event) cudaEventRecord((cudaEvent_t)io.mid_event, s);
     StepDev io2 = io;
     io2.jobs = io.handoff + 1;
     io2.n_jobs = io.handoff;
     io2.handoff = nullptr;
-    launch_lanes<SH, true, false, false>(rf, io2, ro, io.types, n, s);
+    launch_lanes<SH, PHILOX, false, false>(rf, io2, ro, io.types, n, s);
 }
 
 int op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
     const RolloutDev ro = {};
-    if (philox && io.handoff && n <= (1ll << 29)) { // the job cursor's 32-bit arithmetic: 2 n + warps < 2^31
-        if (wide) launch_two_kernel_step<SHW>(rf, io, n, s);
-        else launch_two_kernel_step<SHN>(rf, io, n, s);
+    // (the job cursor's 32-bit arithmetic: 2 n + warps < 2^31)
+    if (io.handoff && n <= (1ll << 29) && (philox || (rf.tiles && rf.tile_wpos))) {
+        if (philox) {
+            if (wide) launch_two_kernel_step<SHW, true>(rf, io, n, s);
+            else launch_two_kernel_step<SHN, true>(rf, io, n, s);
+        } else {
+            if (wide) launch_two_kernel_step<SHW, false>(rf, io, n, s);
+            else launch_two_kernel_step<SHN, false>(rf, io, n, s);
+        }
         return 2;
     }
     io.handoff = nullptr;

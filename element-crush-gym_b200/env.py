@@ -166,8 +166,11 @@ class HostStepper:
         if b.refill_mode == "replay":
             if b.stream_index is not None:
                 rf.stream_index = b.stream_index[lo:].data_ptr()
-            else:
+            elif b.stream_stride:  # chunk [lo, hi) of per-board streams (and of their tile tables)
                 rf.stream = b.stream.data_ptr() + 4 * lo * b.stream_stride
+                if rf.tiles:
+                    rf.tiles = b.tiles.data_ptr() + 4 * lo * (b.tiles.numel() // b.n)
+                    rf.tile_wpos = b.tile_wpos.data_ptr() + 2 * lo * (b.stream_len + 1)
             rf.stream_pos = b.stream_pos[lo:].data_ptr()
         return io, rf
 

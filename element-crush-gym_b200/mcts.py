@@ -138,6 +138,7 @@ class BatchedRolloutMCTS:
         boards, mask, res = state._step(acts, n, torch.zeros(n, dtype=torch.int32, device=dev))
         rest = BatchedBoards(state.cfg, n, state.n_actions - 1, device=dev, refill="replay", _empty=True)
         rest.stream, rest.stream_len, rest.stream_stride = state._stream, state.stream_len, 0  # MT(cfg.seed), shared
+        rest.two_kernel_step = False  # rollouts run in the exact kernel: no tile tables needed
         rest.stream_pos = res[3].contiguous()  # each episode continues where its first step left the stream
         rest.boards = boards
         total = rest.rollout()

@@ -110,6 +110,8 @@ class BoardV2:
         b = BatchedBoards(self.cfg, 1, self.n_actions, device=self.device, refill="replay", seeds=[self.cfg.seed],
                           stream_len=self.stream_len, _empty=True)
         b.stream, b.stream_len, b.stream_stride = self._stream, self.stream_len, 0
+        if b.two_kernel_step:
+            b._build_tiles(1)
         b.stream_pos = torch.full((1,), self.stream_pos, dtype=torch.int32, device=self.device)
         b.boards.copy_(self._boards)
         b.mask.copy_(self._ensure_mask())

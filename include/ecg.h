@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ECG_VERSION 103
+#define ECG_VERSION 104
 
 /* per-board status bits */
 #define ECG_ST_TERMINAL 1        /* n_actions < 1: board returned unchanged (boardv2.py:44-45) */
@@ -72,6 +72,10 @@ typedef struct ecg_refill {
     const int32_t *stream_index; /* replay, optional [n]: board i replays the stream at stream + stream_index[i] *
                                     stream_stride instead of i * stream_stride (children of an expansion keep their
                                     parent's stream, boardv2.py:46: every BoardV2 reseeds with the same cfg.seed) */
+    const uint32_t *tiles;       /* replay, optional: per-stream tile tables made by ecg_replay_tiles from `stream` for this */
+    const uint16_t *tile_wpos;   /* board config's `types`.  With them (and ecg_step_io.scratch) the replay step runs as two
+                                    kernels like the Philox step; results are identical with and without.  Streams must be
+                                    packed (stream_stride == stream_len, or 0 for one shared stream). */
 } ecg_refill;
 
 /* Buffers of one lockstep step.  n-element arrays are plain board-indexed; boards/masks are packed. */
@@ -97,8 +101,8 @@ typedef struct ecg_step_io {
                                  score == NULL (in/out arrays would be read at src_index[i] while job src_index[i]
                                  writes them); replay mode with actions == NULL also needs stream_pos == NULL.  With
                                  explicit actions stream_pos is output only: [i] = words this step consumed. */
-    int32_t *scratch;        /* optional work list, [n + 1] int32, contents irrelevant on entry and exit.  Philox mode
-                                only: when given, the step runs as TWO kernels -- the common-case kernel over all n
+    int32_t *scratch;        /* optional work list, [n + 1] int32, contents irrelevant on entry and exit.  Philox mode, or
+                                replay mode with tile tables (ecg_refill.tiles): when given, the step runs as TWO kernels -- the common-case kernel over all n
                                 boards, which hands the boards that need a rare path (intersecting runs, runs of 6+,
                                 a swap of two special tokens, the shuffle loop; about 5 % of the 9x9x6 steps) over to
                                 the exact kernel through this list.  Results are identical with and without it. */
@@ -138,6 +142,14 @@ int ecg_unpack_mask(const ecg_config *cfg, const uint32_t *mask, uint8_t *out, i
 
 /* raw u32 output of np.random.seed(seed) (numpy legacy MT19937 init_genrand): out[i*len + k] */
 int ecg_mt19937_stream(const uint32_t *seeds, uint32_t *out, int32_t len, int64_t n, void *stream);
+
+/* Tile tables of the replay streams: within one apply_action the refill tiles np.random.randint(1, types + 1)
+ * (boardv2.py:172) are a prefix of the stream's accepted values (masked rejection restarted by np.random.seed,
+ * boardv2.py:46).  tiles: ecg_replay_tiles_words(stream_len) u32 per stream (tile j = nibble j), tile_wpos:
+ * stream_len + 1 u16 per stream (raw words consumed once j tiles are taken).  streams: [n_streams, stream_len]. */
+int64_t ecg_replay_tiles_words(int32_t stream_len);
+int ecg_replay_tiles(const uint32_t *streams, int32_t stream_len, int types, uint32_t *tiles, uint16_t *tile_wpos,
+                     int64_t n_streams, void *stream);
 
 /* BoardV2.__init__ (boardv2.py:20-27): draw boards, redraw matched cells until no match remains.
  * replay: consumes the board's stream from position 0; philox: substream (board, step 0xFFFFFFFF). */

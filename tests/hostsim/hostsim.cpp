@@ -4,6 +4,7 @@
 // nothing under element-crush-gym_b200/ loads this library.
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../element-crush-gym_b200/csrc/ecg_core.cuh"
 
@@ -54,6 +55,7 @@ struct StepArgs {
     uint8_t *status, *legal;
     int64_t n;
     int64_t *handoffs; // modes 3 / 4: incremented per board the common-case build handed off
+    uint32_t *words;   // optional, replay: raw words consumed by the step
 };
 
 template <class SH>
@@ -84,11 +86,19 @@ static void step_t(const StepArgs &a) {
         } else {
             ReplayRng rng;
             rng.init(a.raw + i * a.raw_stride, (uint32_t)a.raw_len, 0);
-            if (a.mode == 3) {
-                if (step_board_two_pass<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL) && a.handoffs)
-                    ++*a.handoffs;
+            if (a.mode == 3) { // the replay two-kernel step: precomputed tiles in the common-case pass
+                std::vector<uint32_t> tiles(replay_tile_words((int)a.raw_len));
+                std::vector<uint16_t> wpos(a.raw_len + 1);
+                build_replay_tiles(a.raw + i * a.raw_stride, (int)a.raw_len, (uint32_t)a.types, tiles.data(), wpos.data());
+                ReplayTileRng frng;
+                frng.init(tiles.data(), wpos.data(), 0);
+                const bool handed_off = step_board_two_pass<SH>(b, a.actions[i], (uint32_t)a.types, frng, rng, so, HL, VL);
+                if (handed_off && a.handoffs) ++*a.handoffs;
+                // np.random's position behind the step: the tile table's word count must equal the exact build's
+                if (a.words) a.words[i] = handed_off ? rng.pos : frng.words();
             } else {
                 step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+                if (a.words) a.words[i] = rng.pos;
             }
         }
         unpack_board<SH>(cc, b, a.out + i * N);
@@ -179,6 +189,7 @@ static void init_t(int types, const uint32_t *raw, int64_t raw_stride, int64_t r
     } while (0)
 
 static int64_t g_handoffs = 0;
+static uint32_t *g_words = nullptr; // hs_set_words: where the next replay hs_step reports the words each step drew
 
 extern "C" {
 
@@ -189,9 +200,12 @@ int hs_step(int rows, int cols, int types, int mode, const uint32_t *raw, int64_
     if (rows != cols || types < 1 || types > 11) return -1;
     g_handoffs = 0;
     StepArgs a = {types, mode, raw, raw_stride, raw_len, key, board0, step_ctr, in, actions, moves_left,
-                  out, reward, cascades, status, legal, n, &g_handoffs};
+                  out, reward, cascades, status, legal, n, &g_handoffs, g_words};
+    g_words = nullptr;
     DISPATCH(rows, types, step_t<SH>(a));
 }
+
+void hs_set_words(uint32_t *words) { g_words = words; }
 
 // boards the common-case build handed off in the last hs_step call (modes 3 / 4)
 int64_t hs_handoffs(void) { return g_handoffs; }

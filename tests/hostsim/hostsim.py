@@ -75,12 +75,15 @@ class HostSim:
         casc = np.zeros(n, dtype=np.int32)
         status = np.zeros(n, dtype=np.uint8)
         legal = np.zeros((n, self.A), dtype=np.uint8)
+        words = np.zeros(n, dtype=np.uint32)
+        if mode == "replay":
+            self.L.hs_set_words(_p(words))
         rc = self.L.hs_step(self.rows, self.cols, self.types, m, _p(raw), C.c_int64(stride), C.c_int64(rawlen),
                             C.c_uint64(key), C.c_uint64(board0), C.c_uint32(step_ctr), _p(boards), _p(actions), _p(ml),
                             _p(out), _p(reward), _p(casc), _p(status), _p(legal), C.c_int64(n))
         assert rc == 0
         return {"boards": out, "reward": reward, "cascades": casc, "status": status, "legal": legal.astype(bool),
-                "handoffs": int(self.L.hs_handoffs())}
+                "handoffs": int(self.L.hs_handoffs()), "words": words}
 
     def legal(self, boards):
         boards = np.ascontiguousarray(boards, dtype=np.int64)

@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol(E):
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(E._native.EXPORTS), declared ^ set(E._native.EXPORTS)
-    assert E._native.lib().ecg_version() == 103
+    assert E._native.lib().ecg_version() == 104
 
 
 def test_struct_layouts_match_header(E):
     N = E._native
     assert C.sizeof(N.Config) == 14 * 4
-    assert C.sizeof(N.Refill) == 64 and N.Refill.stream.offset == 8 and N.Refill.philox_key.offset == 32
-    assert N.Refill.stream_index.offset == 56
+    assert C.sizeof(N.Refill) == 80 and N.Refill.stream.offset == 8 and N.Refill.philox_key.offset == 32
+    assert N.Refill.stream_index.offset == 56 and N.Refill.tiles.offset == 64 and N.Refill.tile_wpos.offset == 72
     assert C.sizeof(N.StepIO) == 12 * 8 + 8 + 8 + 8 and N.StepIO.env_goal.offset == 96 and N.StepIO.src_index.offset == 104
     L = N.lib()
     for which, st in enumerate((N.Config, N.Refill, N.StepIO)):  # ECG_SIZEOF_CONFIG / _REFILL / _STEP_IO

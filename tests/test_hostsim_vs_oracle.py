@@ -162,6 +162,44 @@ def test_two_pass_episodes_philox(shape):
     assert 0 < handoffs < (0.04 if shape == (9, 9, 6) else 0.25) * n * 12
 
 
+@pytest.mark.parametrize("shape", ALL_SHAPES)
+def test_replay_two_pass_tile_tables(shape):
+    """The replay two-kernel step on the host: the common-case pass takes its refill tiles from the per-stream
+    tile table (build_replay_tiles / ReplayTileRng) instead of rejection-sampling raw words.  Boards, rewards, cascade
+    counts, legal sets AND np.random's position behind the step must equal the exact pass and the reference-generated
+    episodes; short streams must overflow exactly like the exact build."""
+    d = load("episodes_%dx%dx%d.npz" % shape)
+    h = HostSim(*shape)
+    seeds = d["seeds"]
+    raw = np.stack([Oracle.mt_raw(int(s), 2048) for s in seeds])
+    boards = d["init"].astype(np.int64)
+    handoffs = 0
+    for t in range(int(d["moves"])):
+        one = h.step(boards, d["actions"][:, t], mode="replay", raw=raw)
+        two = h.step(boards, d["actions"][:, t], mode="replay", raw=raw, two_pass=True)
+        handoffs += two["handoffs"]
+        for k in ("boards", "reward", "cascades", "status", "legal", "words"):
+            assert np.array_equal(one[k], two[k]), (k, t)
+        assert np.array_equal(two["boards"], d["boards"][:, t]) and np.array_equal(two["reward"], d["rewards"][:, t])
+        boards = two["boards"]
+    assert handoffs < len(seeds) * int(d["moves"])  # the tile path was exercised
+    # dense boards with planted specials, one shared stream, and a stream that is too short for some of the steps
+    rng = np.random.default_rng(shape[0] * 7 + shape[2])
+    o = Oracle(*shape)
+    b, _ = _fuzz_boards(rng, o, 1200)
+    acts = rng.integers(0, o.A, size=len(b))
+    for raw1 in (Oracle.mt_raw(99, 2048), Oracle.mt_raw(99, 6), Oracle.mt_raw(5, 1)):
+        one = h.step(b, acts, mode="replay", raw=raw1)
+        two = h.step(b, acts, mode="replay", raw=raw1, two_pass=True)
+        ro = o.step_batch(b, acts, mode="replay", raw=raw1)
+        for k in ("boards", "reward", "cascades", "status", "legal"):
+            assert np.array_equal(one[k], two[k]) and np.array_equal(ro[k], two[k]), (k, len(raw1))
+        ok = (two["status"] & ST_STREAM_OVERFLOW) == 0
+        assert np.array_equal(one["words"][ok], two["words"][ok])
+        if len(raw1) < 10:
+            assert (two["status"] & ST_STREAM_OVERFLOW).any()
+
+
 def test_caps_and_flags():
     # cascade cap: 9x9 with 2 types never settles
     o, h = Oracle(9, 9, 2), HostSim(9, 9, 2)
