@@ -761,6 +761,18 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
             //   x left end, not top (V fires first)     : the two cells right of x stay
             //   neither (merged T / + shape)            : everything cleared, bomb on x -- or on the cell left
             //                                             of x when x is the bottom of V and the right end of H
+#if defined(ECG_FAST_CROSS_CALL)
+            // measured alternative: ONE shared cell with a run of four or more on the board (three quarters of the
+            // hand-offs) resolved here by the exact build's out-of-line closed form instead of a hand-off
+            if (popcount(X) == 1 && any(L4h | L4v)) {
+                const MatchOut<G> o = crossing_matches<SH>(m.A, m.D, hs, vs, H3 | V3, X);
+                m.mask = o.mask;
+                m.sp = o.sp;
+                m.sk0 = o.sk0;
+                m.sk1 = o.sk1;
+                return;
+            }
+#endif
             if (popcount(X) != 1 || any(L4h | L4v)) {
                 ECG_RARE(popcount(X) != 1 ? 0 : 1);
 #if defined(ECG_COUNT_RARE) && !defined(__CUDA_ARCH__)
@@ -1203,14 +1215,15 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
         }
 #endif
     } else if constexpr (UsesTileWindow<RNG>::value) {
-        // the reference's order with precomputed tiles (ReplayTileRng): 16 tiles per window, one nibble per hole
-        uint32_t t = rng.tpos, lo, hi;
+        // the reference's order with precomputed tiles (ReplayTileRng): 16 tiles per window, one nibble per hole.
+        // ONE flat loop, one hole per trip (down the column, then on to the next column with a hole): the nested
+        // column / hole loops of the exact build ran 24 times per warp trip at 5 of 32 lanes (ncu r04c).
         uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
-        if (cols) rng.window(t, lo, hi);
-        while (cols) {
+        if (cols) {
+            uint32_t t = rng.tpos, lo, hi;
+            rng.window(t, lo, hi);
             int bit = ctz32(cols);
-            cols &= cols - 1u;
-            do {
+            for (;;) {
                 if (lo == 0u) rng.window(t, lo, hi); // 16 tiles used up (or the stream: dummies + overflow)
                 const int wi = bit >> 5;
                 const uint32_t m = 1u << (bit & 31);
@@ -1226,9 +1239,13 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
                 hi >>= 4;
                 t++;
                 bit += G::S;
-            } while (bit < G::NB && testbit(holes, bit));
+                if (bit < G::NB && testbit(holes, bit)) continue; // the next hole of this column
+                cols &= cols - 1u;
+                if (!cols) break;
+                bit = ctz32(cols);
+            }
+            rng.tpos = t;
         }
-        rng.tpos = t;
     } else {
         uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
         while (cols) {

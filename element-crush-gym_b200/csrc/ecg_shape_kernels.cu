@@ -405,8 +405,9 @@ constexpr int CHUNK_BOARDS = ECG_CHUNK;
 // at 96 % of peak).  In lockstep a cache line fetched by one warp is reused by the other 15: +11 % env-steps/s
 // (4.39e9 -> 4.87e9 at 9x9x6; 128 x 4 in lockstep: 4.40e9, 256 x 2: 4.84e9, 512 x 1: 4.87e9).
 // Boards of 16x16 (9 words per plane) need ~250 registers: 512-thread blocks (128 registers) spilled 650 B per thread
-// (r04b: 1.42e9 env-steps/s; 256 threads x 255 registers: 1.98e9; 384 x 168: 1.67e9).  12x12 is best at 512.
-#if ECG_SIZE >= 16 && !defined(ECG_LANE_BLOCK) && !defined(ECG_FAST_BLOCK)
+// (r04b: 1.42e9 env-steps/s; 256 threads x 255 registers: 1.98e9; 384 x 168: 1.67e9).  256 also wins at 15x15 (2.04e9 ->
+// 2.54e9) and 14x14 (2.09e9 -> 2.28e9); 13x13 (2.89e9 vs 2.83e9) and 12x12 (3.85e9 vs 3.45e9) are best at 512 (r04c).
+#if ECG_SIZE >= 14 && !defined(ECG_LANE_BLOCK) && !defined(ECG_FAST_BLOCK)
 #define ECG_LANE_BLOCK 256
 #define ECG_FAST_BLOCK 256
 #endif
