@@ -15,6 +15,8 @@ K steps on 2^24 boards IN TOTAL split evenly over the N GPUs (BASELINE configs[2
 
 The JSON line also carries
   sustained    >= 5 s of back-to-back steps with SM clock and power sampled over them (the K-step region is 0.05 s);
+  shape_sweep  BASELINE configs[3]: 6x6x4, 9x9x6, 12x12x7, 16x16x8 at 2^22 boards per GPU, roofline fraction per shape;
+  mcts         BASELINE configs[4]: standard MCTS with 2^20 GPU rollouts per simulation, reward sums over NCCL;
   replay       the REFERENCE's dynamics at the same size: ECG_REFILL_REPLAY, every step restarts the MT19937 stream
                of cfg.seed (boardv2.py:46) -- one stream shared by all boards, and 4096 distinct streams;
   e2e          the same metric through the public host-buffer API (HostStepper): per step the actions are fetched to
@@ -59,6 +61,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--sustained-seconds", type=float, default=5.0)
     ap.add_argument("--replay-steps", type=int, default=12)
+    ap.add_argument("--sweep-boards", type=int, default=1 << 22, help="boards per GPU and shape of the shape sweep")
+    ap.add_argument("--mcts-leaves", type=int, default=1 << 20)
+    ap.add_argument("--mcts-sims", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the strong/weak twin, sustained and replay legs")
@@ -388,6 +393,47 @@ def run_ours(args):
                             "words; rare cases go to lane_kernel<..., replay, step, exact>")
         replay["philox_for_comparison"] = {"mean_cascades_per_step": mean_casc, "mean_reward_per_step": mean_reward}
 
+    # ---- BASELINE configs[3]: the board-shape sweep, each shape with its own roofline (per GPU, shards independent)
+    sweep = None
+    if not args.no_extra_legs and args.sweep_boards > 0:
+        sweep = []
+        peak_gbs, _ = measured_peak()
+        for rows, types in ((6, 4), (9, 6), (12, 7), (16, 8)):
+            cfg_s = E.BoardConfig(seed=5, rows=rows, columns=rows, types=types)
+            sb = E.BatchedBoards(cfg_s, args.sweep_boards, 1 << 30, device=dev, key=99, board0=rank * args.sweep_boards)
+            sb.packed_mask()
+            ms_s, _, _ = timed_steps(sb, 12, 4)
+            bytes_per_step = 2 * ((rows * rows + 1) // 2) + 17 + (cfg_s.action_space + 7) // 8
+            rate = world * args.sweep_boards * 12 / (ms_s * 1e-3)
+            sweep.append({"shape": f"{rows}x{rows}x{types}", "boards_per_gpu": args.sweep_boards, "value": rate,
+                          "unit": UNIT, "ms_per_step": ms_s / 12, "algorithmic_bytes_per_step": bytes_per_step,
+                          "roofline_frac": rate / world * bytes_per_step / 1e9 / peak_gbs,
+                          "mean_cascades_per_step": float(sb.cascades.float().mean().item()),
+                          "handed_off_to_exact_kernel": int(sb._scratch[0].item())})
+            sb = None
+            torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: mctslib standard MCTS, GPU-batched rollouts, reward sums reduced over NCCL
+    mcts_leg = None
+    if not args.no_extra_legs and args.mcts_sims > 0:
+        state = E.BoardV2(20, E.BoardConfig(seed=7), device=dev)
+        m = E.BatchedRolloutMCTS(state, 3, 2, False, leaves=args.mcts_leaves, key=1234)
+        m()  # warm-up: 2 simulations (also re-roots the tree, like the reference's move loop)
+        m._simulations = args.mcts_sims
+        torch.cuda.synchronize(dev)
+        barrier()
+        steps0 = m.env_steps
+        t0 = time.perf_counter()
+        action, value_m, policies = m()
+        torch.cuda.synchronize(dev)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        mcts_leg = {"leaves_per_simulation": args.mcts_leaves, "simulations": args.mcts_sims, "moves": 20,
+                    "ms_per_simulation": dt / args.mcts_sims * 1e3, "leaves_per_s": args.mcts_leaves * args.mcts_sims / dt,
+                    "rollout_env_steps_per_s": (m.env_steps - steps0) / dt, "root_children": len(policies),
+                    "refill": "philox", "reduction": ("NCCL all-reduce of the reward sum per simulation (visit counts "
+                                                      "are known on the host)") if world > 1 else "none (1 GPU)"}
+        m = state = None
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_rate(12.0)
@@ -411,6 +457,7 @@ def run_ours(args):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": cfg, "clocks": clocks, "e2e": e2e, "e2e_nibbles": e2e_nib, "gpu_launches": int(launches),
             ("weak" if strong_main else "strong"): twin, "sustained": sustained, "replay": replay,
+            "shape_sweep": sweep, "mcts": mcts_leg,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch") * scale_traffic,
                          "traffic_source": None if traffic is None else traffic.get("source"),

@@ -286,28 +286,34 @@ struct ReplayTileRng {
     static constexpr bool TILE_WINDOW = true;
     const uint32_t *tiles;
     const uint16_t *wpos;
-    uint32_t tpos; // tiles taken since the last reseed
+    uint32_t tpos, len; // tiles taken since the last reseed; words (= table entries) of the stream
     bool overflow;
-    ECG_HD void init(const uint32_t *tiles_, const uint16_t *wpos_, uint32_t tpos_) {
+    ECG_HD void init(const uint32_t *tiles_, const uint16_t *wpos_, uint32_t len_, uint32_t tpos_) {
         tiles = tiles_;
         wpos = wpos_;
+        len = len_;
         tpos = tpos_;
         overflow = false;
     }
+    // after a refill: were all the tiles taken so far really there?  (a window may end inside the stream's last tiles)
+    ECG_HD void check_end() {
+        if (tpos > len || wpos[tpos > len ? len : tpos] == REPLAY_TILES_END) overflow = true;
+    }
     ECG_HD void reseed() { tpos = 0; }
     ECG_HD void seek(uint32_t) {}
-    // the 16 tiles from tile t on, one per nibble, first in the low nibble of lo; past the end of the stream the
-    // window is filled with dummies and overflow is set (the caller drops the board)
+    // the 16 tiles from tile t on, one per nibble, first in the low nibble of lo (zero nibbles past the stream's
+    // last tile: check_end() after the refill tells)
     ECG_HD void window(uint32_t t, uint32_t &lo, uint32_t &hi) {
+        if (t >= len) { // the table holds at most len tiles
+            overflow = true;
+            lo = hi = 0x11111111u;
+            return;
+        }
         const uint32_t *p = tiles + (t >> 3);
         const int sh = (int)(t & 7u) * 4;
         const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
         lo = funnel_r(w0, w1, sh);
         hi = funnel_r(w1, w2, sh);
-        if ((lo & 15u) == 0u) {
-            overflow = true;
-            lo = hi = 0x11111111u;
-        }
     }
     ECG_HD uint32_t words() const { return wpos[tpos]; } // raw words behind the tiles taken (np.random's position)
 };
@@ -1216,35 +1222,42 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
 #endif
     } else if constexpr (UsesTileWindow<RNG>::value) {
         // the reference's order with precomputed tiles (ReplayTileRng): 16 tiles per window, one nibble per hole.
-        // ONE flat loop, one hole per trip (down the column, then on to the next column with a hole): the nested
-        // column / hole loops of the exact build ran 24 times per warp trip at 5 of 32 lanes (ncu r04c).
+        // ONE flat loop, one hole per trip, the next hole chosen without a branch (down the column, else the top of
+        // the next column with a hole): as nested column / hole loops the lanes of a warp waited for each other at
+        // every column change (24 trips per warp iteration at 5 of 32 lanes, ncu r04c / r04d).
         uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
         if (cols) {
-            uint32_t t = rng.tpos, lo, hi;
-            rng.window(t, lo, hi);
+            uint32_t t = rng.tpos;
             int bit = ctz32(cols);
-            for (;;) {
-                if (lo == 0u) rng.window(t, lo, hi); // 16 tiles used up (or the stream: dummies + overflow)
-                const int wi = bit >> 5;
-                const uint32_t m = 1u << (bit & 31);
+            bool more = true;
+            do { // one window of 16 tiles per pass: a second pass is rare
+                uint32_t lo, hi;
+                rng.window(t, lo, hi);
+                t += 16u;
+                int left = 16;
+                do {
+                    const int wi = bit >> 5;
+                    const uint32_t m = 1u << (bit & 31);
 #pragma unroll
-                for (int i = 0; i < G::W; i++) {
-                    const uint32_t mi = (i == wi) ? m : 0u;
-                    deposit_bit<1>(b.p[0].w[i], lo, mi);
-                    deposit_bit<2>(b.p[1].w[i], lo, mi);
-                    deposit_bit<4>(b.p[2].w[i], lo, mi);
-                    if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[i], lo, mi);
-                }
-                lo = funnel_r(lo, hi, 4);
-                hi >>= 4;
-                t++;
-                bit += G::S;
-                if (bit < G::NB && testbit(holes, bit)) continue; // the next hole of this column
-                cols &= cols - 1u;
-                if (!cols) break;
-                bit = ctz32(cols);
-            }
-            rng.tpos = t;
+                    for (int i = 0; i < G::W; i++) {
+                        const uint32_t mi = (i == wi) ? m : 0u;
+                        deposit_bit<1>(b.p[0].w[i], lo, mi);
+                        deposit_bit<2>(b.p[1].w[i], lo, mi);
+                        deposit_bit<4>(b.p[2].w[i], lo, mi);
+                        if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[i], lo, mi);
+                    }
+                    lo = funnel_r(lo, hi, 4);
+                    hi >>= 4;
+                    const int nb = bit + G::S;
+                    const bool down = testbit(holes, nb); // (bits past the board are never set)
+                    const uint32_t rest = cols & (cols - 1u);
+                    more = down || rest != 0u;
+                    cols = down ? cols : rest;
+                    bit = down ? nb : ctz32(rest | 0x80000000u);
+                } while (more && --left);
+            } while (more);
+            rng.tpos += (uint32_t)popcount(holes);
+            rng.check_end();
         }
     } else {
         uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity

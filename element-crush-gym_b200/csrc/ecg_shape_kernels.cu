@@ -678,7 +678,8 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                 rng.preset_block(blk_index, blk);
             } else if constexpr (FAST) { // rpos counts TILES while the step is in flight (converted at the end)
                 const long long sid = stream_id(rf, src);
-                rng.init(rf.tiles + sid * replay_tile_words(rf.stream_len), rf.tile_wpos + sid * (rf.stream_len + 1), rpos);
+                rng.init(rf.tiles + sid * replay_tile_words(rf.stream_len), rf.tile_wpos + sid * (rf.stream_len + 1),
+                         (uint32_t)rf.stream_len, rpos);
             } else {
                 rng.init(stream_of(rf, src), (uint32_t)rf.stream_len, rpos);
             }

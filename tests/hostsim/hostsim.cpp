@@ -91,7 +91,7 @@ static void step_t(const StepArgs &a) {
                 std::vector<uint16_t> wpos(a.raw_len + 1);
                 build_replay_tiles(a.raw + i * a.raw_stride, (int)a.raw_len, (uint32_t)a.types, tiles.data(), wpos.data());
                 ReplayTileRng frng;
-                frng.init(tiles.data(), wpos.data(), 0);
+                frng.init(tiles.data(), wpos.data(), (uint32_t)a.raw_len, 0);
                 const bool handed_off = step_board_two_pass<SH>(b, a.actions[i], (uint32_t)a.types, frng, rng, so, HL, VL);
                 if (handed_off && a.handoffs) ++*a.handoffs;
                 // np.random's position behind the step: the tile table's word count must equal the exact build's

@@ -587,6 +587,66 @@ def test_unpack_uint8_partial_tiles_stay_in_bounds(E):
             assert bool((buf[cells:] == 0xAB).all()), (shape, n)
 
 
+GUARDED = ("boards", "mask", "moves_left", "score", "step_reward", "cascades", "flags", "status", "last_actions",
+           "_scratch", "stream_pos")
+
+
+def guard(bb, G=256):
+    """Re-home every device buffer the step kernels touch between two sentinel bands.  compute-sanitizer is closed on
+    this GPU pool, so out-of-bounds WRITES are caught this way: any store past either end of a buffer lands in a band."""
+    import torch
+    bands = []
+    for name in GUARDED:
+        t = getattr(bb, name, None)
+        if t is None:
+            continue
+        fill = 0x5A if t.dtype == torch.uint8 else 0x5A5A5A5A if t.dtype == torch.int32 else 0x5A5A
+        big = torch.full((t.numel() + 2 * G,), fill, dtype=t.dtype, device=t.device)
+        big[G:G + t.numel()].copy_(t.reshape(-1))
+        setattr(bb, name, big[G:G + t.numel()].view(t.shape))
+        bands.append((name, big, G, fill))
+    return bands
+
+
+def check_guard(bands):
+    for name, big, G, fill in bands:
+        assert bool((big[:G] == fill).all()) and bool((big[-G:] == fill).all()), f"out-of-bounds write around {name}"
+
+
+@pytest.mark.parametrize("shape", [(9, 9, 6), (16, 16, 8), (6, 6, 4), (13, 13, 9)])
+@pytest.mark.parametrize("n", [1, 33, 2048 + 13])
+def test_no_out_of_bounds_writes(E, shape, n):
+    """Every kernel of the step path with its buffers between sentinel bands: two-kernel Philox and replay steps
+    (hand-off list), explicit actions, whole-episode rollouts, expand() through src_index, observations."""
+    import torch
+    cfg = cfg_of(E, shape)
+    o = Oracle(*shape)
+    for mode in ("philox", "replay"):
+        kw = dict(key=KEY) if mode == "philox" else dict(refill="replay", seeds=list(range(7, 7 + n)), stream_len=1024)
+        bb = E.BatchedBoards(cfg, n, 5, **kw)
+        bands = guard(bb)
+        before = np_(bb.array)
+        bb.apply_action(None)
+        a = np_(bb.last_actions)
+        bb.apply_action(bb.random_action())
+        child, parent, action = bb.expand()
+        cb = guard(child)
+        child.apply_action(None)
+        roll = bb.clone()
+        rb = guard(roll)
+        roll.rollout()
+        obs = torch.full((n * shape[0] * shape[1] + 512,), 0x5A, dtype=torch.uint8, device=bb.device)
+        bb.observe(torch.uint8, out=obs[256:256 + n * shape[0] * shape[1]].view(n, shape[0], shape[1]))
+        torch.cuda.synchronize()
+        check_guard(bands), check_guard(cb), check_guard(rb)
+        assert bool((obs[:256] == 0x5A).all()) and bool((obs[-256:] == 0x5A).all())
+        if mode == "philox":  # and the results are still the oracle's
+            res = o.step_batch(before, a, mode="philox", key=KEY, board0=0, step_ctr=0)
+            again = E.BatchedBoards(cfg, n, 5, arrays=before, key=KEY)
+            again.apply_action(a.astype(np.int32))
+            assert np.array_equal(np_(again.array), res["boards"])
+
+
 def test_onehot_observation(E):
     import torch
     for shape in ((9, 9, 6), (16, 16, 8), (6, 6, 4)):
