@@ -19,6 +19,27 @@ def shard_range(total: int, world: int, rank: int):
     return first, count
 
 
+def bind_to_gpu_numa_node(index: int) -> bool:
+    """Pin this process to the CPUs next to GPU `index` (NVML's ideal CPU affinity) before any pinned host buffer is
+    allocated: pages of cudaHostAlloc memory land on the allocating thread's NUMA node, and a D2H stream that crosses
+    the socket interconnect runs at a fraction of the PCIe rate (bench.py e2e with 2+ ranks on a 2-socket host).
+    Returns False (and changes nothing) when NVML or sched_setaffinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def init_from_env(backend: str = None):
     """Join the process group described by RANK / WORLD_SIZE / MASTER_* (torchrun); no-op when single."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -31,6 +52,8 @@ def init_from_env(backend: str = None):
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
+            if os.environ.get("ECG_NUMA_BIND", "0") == "1":  # opt-in: the pool's boxes are single-node VMs (no effect, r04e)
+                bind_to_gpu_numa_node(local)
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
