@@ -767,10 +767,16 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
             //   x left end, not top (V fires first)     : the two cells right of x stay
             //   neither (merged T / + shape)            : everything cleared, bomb on x -- or on the cell left
             //                                             of x when x is the bottom of V and the right end of H
+            // ONE shared cell with a run of four or more on the board is three quarters of the hand-offs.  On small
+            // boards, which hand off ten times as often (6x6x4: 4.8 % of the steps against 0.55 % at 9x9x6), it is
+            // resolved here by the exact build's out-of-line closed form: 4.85e9 -> 5.10e9 env-steps/s at 6x6x4;
+            // at 9x9x6 the call costs the common-case kernel more than the exact kernel saves (7.19e9 -> 7.00e9, r04d).
 #if defined(ECG_FAST_CROSS_CALL)
-            // measured alternative: ONE shared cell with a run of four or more on the board (three quarters of the
-            // hand-offs) resolved here by the exact build's out-of-line closed form instead of a hand-off
-            if (popcount(X) == 1 && any(L4h | L4v)) {
+            constexpr bool CROSS_CALL = true;
+#else
+            constexpr bool CROSS_CALL = G::R <= 6;
+#endif
+            if (CROSS_CALL && popcount(X) == 1 && any(L4h | L4v)) {
                 const MatchOut<G> o = crossing_matches<SH>(m.A, m.D, hs, vs, H3 | V3, X);
                 m.mask = o.mask;
                 m.sp = o.sp;
@@ -778,7 +784,6 @@ ECG_PHASE void find_matches(const Derived<typename SH::G> &d, Matches<typename S
                 m.sk1 = o.sk1;
                 return;
             }
-#endif
             if (popcount(X) != 1 || any(L4h | L4v)) {
                 ECG_RARE(popcount(X) != 1 ? 0 : 1);
 #if defined(ECG_COUNT_RARE) && !defined(__CUDA_ARCH__)
