@@ -431,6 +431,46 @@ def test_full_size_properties(E):
     assert torch.equal(m1, bb.packed_mask())
 
 
+def test_full_size_replay_properties(E):
+    """The reference's dynamics at BASELINE configs[2] size: 2^24 boards, two-kernel replay step, 4096 distinct MT19937
+    streams; a strided sample is checked against the oracle (boards, rewards, np.random's position), the rest through
+    size-independent properties."""
+    import torch
+    n, streams, moves = 1 << 24, 4096, 2
+    shape = (9, 9, 6)
+    o = Oracle(*shape)
+    src = E.BatchedBoards(cfg_of(E, shape), n, 9, key=KEY)
+    dev = src.device
+    bb = E.BatchedBoards(cfg_of(E, shape), n, 9, refill="replay", stream_len=1024,
+                         seeds=[1000 + i for i in range(streams)],
+                         stream_index=torch.arange(n, device=dev).remainder(streams))
+    assert bb.two_kernel_step and bb.tiles is not None
+    bb.boards.copy_(src.boards)
+    del src
+    bb._mask_valid = False
+    idx = torch.arange(0, n, 65537, device=dev)
+    raw = np.stack([Oracle.mt_raw(1000 + int(i) % streams, 1024) for i in np_(idx)])
+    sample = np_(bb.array[idx])
+    acc = torch.zeros(n, dtype=torch.int64, device=dev)
+    for t in range(moves):
+        bb.apply_action(None)
+        acc += bb.step_reward
+        a = np_(bb.last_actions[idx])
+        res = o.step_batch(sample, a, mode="replay", raw=raw)
+        assert not res["status"].any()
+        assert np.array_equal(np_(bb.array[idx]), res["boards"])
+        assert np.array_equal(np_(bb.step_reward[idx]), res["reward"])
+        assert np.array_equal(np_(bb.cascades[idx]), res["cascades"])
+        sample = res["boards"]
+        st = bb.status
+        assert not bool((st & ~(E.ST_NO_LEGAL | E.ST_SHUFFLE_CAP)).any())
+        obs = bb.observe(torch.uint8)
+        assert int(obs.min()) >= 1 and int(obs.max()) <= 32
+        assert int(bb.stream_pos.min()) >= 1 or bool(((st & E.ST_NO_LEGAL) != 0).any())  # every step drew tiles
+    assert torch.equal(acc, bb.reward)
+    assert 1.6 < float(bb.cascades.float().mean()) < 2.0  # the reference's heavier cascade load (Philox: 1.53)
+
+
 def test_expand_and_greedy_vs_oracle(E):
     """All legal children of every board in one kernel (Node.expand / greedy_action, boardv2.py:209-218)."""
     shape = (9, 9, 6)
