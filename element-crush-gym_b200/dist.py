@@ -78,8 +78,9 @@ def reduce_stats(stats: torch.Tensor) -> torch.Tensor:
 def reduce_visit_counts(visits: torch.Tensor, reward_sums: torch.Tensor):
     """Sum per-root-child visit counts and reward sums over ranks (MCTS backprop, abc/mcts.py:105-107)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(visits, op=dist.ReduceOp.SUM)
-        dist.all_reduce(reward_sums, op=dist.ReduceOp.SUM)
+        for t in (visits, reward_sums):
+            if t.numel():
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return visits, reward_sums
 
 

@@ -34,8 +34,11 @@ from typing import Optional
 
 import torch
 
+import ctypes as C
+
+from . import _native as N
 from . import dist as ecg_dist
-from .boards import BatchedBoards
+from .boards import BatchedBoards, _ptr, _stream
 from .state import BoardV2
 
 
@@ -85,6 +88,20 @@ class Node:
         return max(self.children.values(), key=lambda child: child.ucb1(c))
 
 
+class _LeafBuffers:
+    """device buffers of one rank's share of the leaves, allocated once per search: a simulation only refills them
+    (one copy of the leaf board into every lane, one fill of moves_left) and launches ecg_rollout"""
+
+    def __init__(self, cfg, count: int, device):
+        self.count = count
+        L = N.lib()
+        nat = cfg.native
+        self.boards = torch.zeros(L.ecg_boards_bytes(C.byref(nat), count) // 4, dtype=torch.int32, device=device)
+        self.moves_left = torch.zeros(count, dtype=torch.int32, device=device)
+        self.total = torch.zeros(count, dtype=torch.int64, device=device)
+        self.steps = torch.zeros(count, dtype=torch.int32, device=device)
+
+
 def replicate(state: BoardV2, n: int, *, key: int, board0: int, device=None) -> BatchedBoards:
     """n copies of one board as a Philox-mode batch (copy i is global board board0 + i)."""
     out = BatchedBoards(state.cfg, n, state.n_actions, device=device or state.device, refill="philox", key=key,
@@ -112,25 +129,13 @@ class BatchedRolloutMCTS:
         self.key = int(key)
         self.refill = refill
         self._sim_counter = 0
-        self._steps_dev = None  # env-steps simulated on this rank, accumulated on the device
+        self.env_steps = 0  # env-steps simulated on the devices so far, over all ranks
+        self._leaf = None   # _LeafBuffers of this rank
         self._root.expand()  # abc/mcts.py:82
-
-    @property
-    def env_steps(self) -> int:
-        """env-steps simulated on the device so far, over all ranks (one read; not on the search path)"""
-        if self._steps_dev is None:
-            return 0
-        t = self._steps_dev.clone()
-        ecg_dist.reduce_visit_counts(t, t.new_zeros(1))
-        return int(t.item())
-
-    def _count_steps(self, steps: torch.Tensor):
-        s = steps.sum().to(torch.int64).reshape(1)
-        self._steps_dev = s if self._steps_dev is None else self._steps_dev + s
 
     def _first_action_returns(self, state: BoardV2) -> torch.Tensor:
         """refill="replay": final cumulative reward of the reference's rollout for every legal first action of
-        `state`, int64 [L] on the device (standard/mcts.py:16-18 over boardv2.py:46)."""
+        `state`, int64 [L] on the device (standard/mcts.py:16-18 over boardv2.py:46), and the env-steps simulated."""
         legal = state.legal_actions
         dev = state.device
         n = len(legal)
@@ -142,8 +147,7 @@ class BatchedRolloutMCTS:
         rest.stream_pos = res[3].contiguous()  # each episode continues where its first step left the stream
         rest.boards = boards
         total = rest.rollout()
-        self._count_steps(rest.rollout_steps + 1)
-        return total + res[0].to(torch.int64) + int(state.reward)
+        return total + res[0].to(torch.int64) + int(state.reward), (rest.rollout_steps.sum() + n).to(torch.int64)
 
     def rollout(self, state: BoardV2):
         """-> (sum of final rewards, number of rollouts) over all ranks"""
@@ -154,15 +158,25 @@ class BatchedRolloutMCTS:
         sim = self._sim_counter
         self._sim_counter += 1
         dev = state.device
+        steps = torch.zeros((), dtype=torch.int64, device=dev)
         if count == 0 or state.is_terminal or (self.refill == "replay" and not state.legal_actions):
-            rsum = torch.tensor([int(state.reward) * count], dtype=torch.int64, device=dev)
+            rsum = torch.tensor(int(state.reward) * count, dtype=torch.int64, device=dev)
         elif self.refill == "philox":
-            batch = replicate(state, count, key=self.key, board0=sim * self.leaves + first)
-            total = batch.rollout()
-            self._count_steps(batch.rollout_steps)
-            rsum = (total.sum() + int(state.reward) * count).reshape(1)
+            if self._leaf is None or self._leaf.count != count:
+                self._leaf = _LeafBuffers(state.cfg, count, dev)
+            lb, nat = self._leaf, state.cfg.native
+            words = nat.board_words
+            tile = state._boards.view(words // 4, 32, 4)  # [chunk, lane, 4 words]; the board sits in lane 0
+            lb.boards.view(-1, 32 * words)[:] = tile[:, :1, :].expand(words // 4, 32, 4).reshape(-1)
+            lb.moves_left.fill_(state.n_actions)
+            rf = N.Refill()
+            rf.mode, rf.philox_key, rf.board0, rf.step_ctr = N.REFILL_PHILOX, self.key, sim * self.leaves + first, 0
+            N.check(N.lib().ecg_rollout(C.byref(nat), C.byref(rf), _ptr(lb.boards), _ptr(lb.moves_left), _ptr(lb.total),
+                                        _ptr(lb.steps), None, count, _stream(dev)), "ecg_rollout")
+            rsum = lb.total.sum() + int(state.reward) * count
+            steps = lb.steps.sum().to(torch.int64)
         else:
-            returns = self._first_action_returns(state)  # [L]
+            returns, steps = self._first_action_returns(state)  # [L]
             n = returns.numel()
             if self.deterministic:  # np.random.seed(cfg.seed); np.random.choice(legal): one fixed first pick
                 import numpy as np
@@ -172,10 +186,13 @@ class BatchedRolloutMCTS:
                 g = torch.Generator(device="cpu")
                 g.manual_seed((self.key * 1000003 + sim * 8191 + rank) & (2 ** 63 - 1))
                 picks = torch.bincount(torch.randint(n, (count,), generator=g), minlength=n).to(dev)
-            rsum = (picks * returns).sum().reshape(1)
-        visits = torch.zeros(1, dtype=torch.int64, device=dev)  # known on the host: nothing to reduce or read
-        ecg_dist.reduce_visit_counts(visits, rsum)
-        return int(rsum.item()), self.leaves
+            rsum = (picks * returns).sum()
+        # one reduction, one device-to-host read per simulation: (reward sum, env-steps); visits are known on the host
+        both = torch.stack([rsum.to(torch.int64).reshape(()), steps.reshape(())])
+        ecg_dist.reduce_visit_counts(both, both[:0])
+        rsum_h, steps_h = both.tolist()
+        self.env_steps += steps_h
+        return rsum_h, self.leaves
 
     def __call__(self):
         node = self._root

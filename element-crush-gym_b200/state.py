@@ -176,9 +176,18 @@ class BoardV2:
             raise KeyError(action)
         table = _actions_table(self.device, self.cfg.action_space)
         boards, mask, res = self._step(table[int(action):], 1)
-        reward, cascades, status, drawn = (int(x[0]) for x in res.tolist())  # the one synchronisation of the step
+        # the new state's legal set rides along: (reward, cascades, status, words drawn) and the action-ordered
+        # legal bytes leave the device in ONE copy -- the one synchronisation of the step
+        A = self.cfg.action_space
+        out = torch.empty(16 + A, dtype=torch.uint8, device=self.device)
+        out[:16].view(torch.int32).copy_(res.reshape(-1))
+        N.check(self._L.ecg_unpack_mask(C.byref(self._nat), _ptr(mask), C.c_void_p(out.data_ptr() + 16), 1,
+                                        _stream(self.device)), "ecg_unpack_mask")
+        host = out.cpu()
+        reward, cascades, status, drawn = host[:16].view(torch.int32).tolist()
         nxt = BoardV2(self.n_actions - 1, self.cfg, device=self.device, stream_len=self.stream_len,
                       _packed=(boards, mask, True))
+        nxt._actions = torch.nonzero(host[16:], as_tuple=False).flatten().tolist()
         nxt._reward = self._reward + reward
         nxt.stream_pos, nxt.last_cascades, nxt.last_status = drawn, cascades, status
         # the reference drew from the global generator after np.random.seed(cfg.seed) (boardv2.py:46, :172;
