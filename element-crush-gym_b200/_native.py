@@ -69,6 +69,8 @@ EXPORTS = {
     "ecg_step_mark_event": (C.c_int, [C.c_void_p]),
     "ecg_rollout": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_int64, C.c_void_p]),
+    "ecg_rollout_scratch": (C.c_int, [C.POINTER(Config), C.POINTER(Refill), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_episode_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_augment": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int64, C.c_void_p]),
     "ecg_observe_onehot": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),

@@ -243,9 +243,10 @@ class BatchedBoards:
         total = torch.empty(self.n, dtype=torch.int64, device=self.device)
         steps = torch.empty(self.n, dtype=torch.int32, device=self.device)
         rf = self._refill()
-        N.check(self.L.ecg_rollout(C.byref(self.nat), C.byref(rf), _ptr(self.boards), _ptr(self.moves_left),
-                                   _ptr(total), _ptr(steps), _ptr(self.status), self.n, _stream(self.device)),
-                "ecg_rollout")
+        scratch = self._scratch if self.refill_mode == "philox" else None  # work list of the two-kernel rollout
+        N.check(self.L.ecg_rollout_scratch(C.byref(self.nat), C.byref(rf), _ptr(self.boards), _ptr(self.moves_left),
+                                           _ptr(total), _ptr(steps), _ptr(self.status), _ptr(scratch), self.n,
+                                           _stream(self.device)), "ecg_rollout")
         self.step_ctr += self._moves_bound  # no board plays more moves than that: no device read, no sync
         self._moves_bound = 0
         self.score += total.to(torch.int32)

@@ -374,15 +374,23 @@ int ecg_step(const ecg_config *cfg, const ecg_refill *rf, const ecg_step_io *io,
     return check_launch("ecg_step");
 }
 
-int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
-                int64_t *total_reward, int32_t *steps_done, uint8_t *status, int64_t n, void *stream) {
+int ecg_rollout_scratch(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
+                        int64_t *total_reward, int32_t *steps_done, uint8_t *status, int32_t *scratch, int64_t n,
+                        void *stream) {
     if (check_cfg(cfg) || check_refill(rf)) return -1;
     if (!boards || !moves_left || !total_reward) return fail("ecg_rollout: boards, moves_left and total_reward are required");
     if (n <= 0) return 0;
     if (n > (1ll << 30)) return fail("ecg_rollout: at most 2^30 boards per call");
-    ops_for(cfg->rows)->rollout(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), boards, moves_left,
-                                (long long *)total_reward, steps_done, status, cfg->types, n, (cudaStream_t)stream);
+    const int launched = ops_for(cfg->rows)->rollout(cfg->types >= 8, rf->mode == ECG_REFILL_PHILOX, to_dev(rf), boards,
+                                                     moves_left, (long long *)total_reward, steps_done, status, scratch,
+                                                     cfg->types, n, (cudaStream_t)stream);
+    g_launches.fetch_add(launched - 1, std::memory_order_relaxed);
     return check_launch("ecg_rollout");
+}
+
+int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
+                int64_t *total_reward, int32_t *steps_done, uint8_t *status, int64_t n, void *stream) {
+    return ecg_rollout_scratch(cfg, rf, boards, moves_left, total_reward, steps_done, status, nullptr, n, stream);
 }
 
 int ecg_observe_onehot(const ecg_config *cfg, const void *boards, void *out, int channels, int elem_kind, int64_t n,

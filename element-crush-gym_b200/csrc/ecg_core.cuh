@@ -903,33 +903,29 @@ ECG_PHASE void swaps_to_actions(const BB<G::W> &HL, const BB<G::W> &VL, uint32_t
     }
 }
 
+// legal_actions[k] (ascending ACTION order, what np.random.choice indexes) straight from the swap bitboards: board
+// row r owns actions r*ROWA ..: its C-1 horizontal swaps, then its C vertical swaps (boardConfig.py:45-59).  One pass
+// over the rows instead of building the action-ordered mask first.
 template <class G>
-ECG_HD int mask_count(const uint32_t m[G::AW]) {
-    int n = 0;
-#pragma unroll
-    for (int i = 0; i < G::AW; i++) n += popc32(m[i]);
-    return n;
-}
-// index of the k-th (0-based) set bit, ascending == legal_actions[k]
-template <class G>
-ECG_HD int mask_select(const uint32_t m[G::AW], int k) {
-    int base = 0;
+ECG_HD int swaps_select_action(const BB<G::W> &HL, const BB<G::W> &VL, int k) {
+    constexpr uint32_t HM = (1u << (G::C - 1)) - 1u, VM = (1u << G::C) - 1u;
     uint32_t w = 0;
+    int base = 0;
     bool done = false;
 #pragma unroll
-    for (int i = 0; i < G::AW; i++) {
-        const int c = popc32(m[i]);
+    for (int r = 0; r < G::R; r++) {
+        const uint32_t row = (extract32(HL, r * G::S) & HM) | ((extract32(VL, r * G::S) & VM) << (G::C - 1));
+        const int c = popc32(row);
         if (!done) {
             if (k < c) {
-                w = m[i];
-                base = 32 * i;
+                w = row;
+                base = r * G::ROWA;
                 done = true;
             } else {
                 k -= c;
             }
         }
     }
-    // k-th set bit of w by bisection on popcounts (no data-dependent loop)
     int pos = 0, c;
     c = popc32(w & 0xFFFFu);
     if (k >= c) { k -= c; pos += 16; w >>= 16; }

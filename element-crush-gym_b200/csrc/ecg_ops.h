@@ -52,9 +52,9 @@ struct ShapeOps {
     void (*random_action)(bool philox, RefillDev rf, const uint32_t *mask, int32_t *actions, uint8_t *status,
                           long long n, cudaStream_t s);
     int (*step)(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s); // kernels launched
-    void (*rollout)(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left,
-                    long long *total_reward, int32_t *steps_done, uint8_t *status, int types, long long n,
-                    cudaStream_t s);
+    int (*rollout)(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left,
+                   long long *total_reward, int32_t *steps_done, uint8_t *status, int32_t *scratch, int types,
+                   long long n, cudaStream_t s); // kernels launched
     void (*onehot)(const void *boards, void *out, int channels, int elem_kind, int types, long long n, cudaStream_t s);
     void (*augment)(const void *boards_in, void *boards_out, bool mirror, bool remap, CodeLut lut, long long n,
                     cudaStream_t s);

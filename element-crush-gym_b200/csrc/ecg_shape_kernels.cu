@@ -359,9 +359,7 @@ __global__ void __launch_bounds__(BLOCK) random_action_kernel(RefillDev rf, cons
     } else { // np.random.choice(legal_actions): k-th legal action in ascending action order
         ReplayRng rng;
         rng.init(stream_of(rf, i), (uint32_t)rf.stream_len, rf.stream_pos ? rf.stream_pos[i] : 0u);
-        uint32_t m[G::AW];
-        swaps_to_actions<G>(HL, VL, m);
-        a = mask_select<G>(m, (int)rng.below((uint32_t)cnt));
+        a = swaps_select_action<G>(HL, VL, (int)rng.below((uint32_t)cnt));
         if (rf.stream_pos) rf.stream_pos[i] = rng.pos;
         if (rng.overflow) st = ST_STREAM_OVERFLOW;
     }
@@ -484,8 +482,8 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
     using G = typename SH::G;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int IDLE = 0, READY = 1, ACTIVE = 2;
-    static_assert(!(FAST && ROLLOUT), "the hand-off is per step");
-    if constexpr (!FAST && !ROLLOUT)
+    static_assert(!(FAST && ROLLOUT && !PHILOX), "two-kernel rollouts are Philox-mode only");
+    if constexpr (!FAST)
         if (io.n_jobs) n = *io.n_jobs;
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * lane_block(FAST) + threadIdx.x) >> 5);
@@ -493,7 +491,7 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
     // ONE contiguous range of (almost) the same length.  Chunks of 32 handed round-robin left some warps with 64 jobs and
     // others with 32 (6.98e9 env-steps/s at 9x9x6; chunks of 16: 7.11e9; equal ranges: 7.18e9).
     const int nwarps_all = (int)((gridDim.x * lane_block(FAST)) >> 5);
-    const int CHUNK = (!FAST && !ROLLOUT && io.n_jobs) ? (n + nwarps_all - 1) / nwarps_all + (n == 0) : ::CHUNK_BOARDS;
+    const int CHUNK = (!FAST && io.n_jobs) ? (n + nwarps_all - 1) / nwarps_all + (n == 0) : ::CHUNK_BOARDS;
     const int stride = (int)((gridDim.x * lane_block(FAST)) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
     int chunk0 = warp * CHUNK;
@@ -550,7 +548,8 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
             const int pf = next + lane;
             if (need && pf < end && !io.src_index) {
                 constexpr int CH = G::W;
-                const uint4 *bp = reinterpret_cast<const uint4 *>(io.boards_in) + (long long)(pf >> 5) * (CH * 32) + (pf & 31);
+                const void *pfb = ROLLOUT ? (const void *)ro.boards : io.boards_in;
+                const uint4 *bp = reinterpret_cast<const uint4 *>(pfb) + (long long)(pf >> 5) * (CH * 32) + (pf & 31);
 #pragma unroll
                 for (int k = 0; k < CH; k++) asm volatile("prefetch.global.L1 [%0];" ::"l"(bp + k * 32));
                 // (prefetching the mask / action / moves / score lines as well measured 0.5 % slower, r03c)
@@ -559,7 +558,7 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
         // ---- LOAD: IDLE -> READY
         if (state == IDLE && cand < n) {
             idx = cand;
-            if constexpr (!FAST && !ROLLOUT)
+            if constexpr (!FAST)
                 if (io.jobs) idx = io.jobs[cand];
             src = idx;
             if constexpr (!ROLLOUT)
@@ -574,6 +573,14 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                 total = 0;
                 steps_done = 0;
                 st_acc = 0;
+                if constexpr (!FAST)
+                    if (io.jobs) { // an episode the common-case rollout kernel handed over: go on where it stopped
+                        steps_done = ro.steps_done[idx];
+                        total = ro.total_reward[idx];
+                        st_acc = ro.status ? ro.status[idx] : 0u;
+                        moves -= steps_done;
+                        step += (uint32_t)steps_done;
+                    }
                 legal_of<SH>(L.bd, HL, VL);
             } else {
                 load_board<G>(io.boards_in, src, L.bd);
@@ -626,9 +633,7 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                 } else { // np.random.choice(legal_actions): ascending action order, numpy's masked rejection
                     ReplayRng rng;
                     rng.init(stream_of(rf, src), (uint32_t)rf.stream_len, rpos);
-                    uint32_t m[G::AW];
-                    swaps_to_actions<G>(HL, VL, m);
-                    action = mask_select<G>(m, (int)rng.below((uint32_t)c));
+                    action = swaps_select_action<G>(HL, VL, (int)rng.below((uint32_t)c));
                     rpos = rng.pos;
                     if (rng.overflow) st = ST_STREAM_OVERFLOW;
                 }
@@ -640,6 +645,10 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                     decode_action<G>(action, b1, b2);
                     d = b2 - b1;
                 }
+                // a rollout that may hand this step over keeps the board of the step's start in HBM (the first step's
+                // is still there): the exact kernel resumes the episode from it
+                if constexpr (ROLLOUT && FAST)
+                    if (steps_done > 0) store_board<G>(ro.boards, idx, L.bd);
                 handoff = step_begin_at<SH, FAST>(L, b1, d);
                 L.status |= st;
                 moves -= 1;
@@ -666,7 +675,7 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
             if (!__any_sync(FULL, state != IDLE || handoff)) break;
 #endif
         } else {
-            if (!ROLLOUT && io.n_jobs) { // the short job list of a two-kernel step: too few trips to pay for barriers
+            if (io.n_jobs) { // the short job list of a two-kernel step / rollout: too few trips to pay for barriers
                 if (!__any_sync(FULL, state != IDLE)) break;
             } else if (!ECG_TRIP_ANY(state != IDLE)) break;
         }
@@ -710,7 +719,14 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
                 int base = 0;
                 if (lane == __ffs((int)hm) - 1) base = atomicAdd(io.handoff, __popc(hm));
                 base = __shfl_sync(FULL, base, __ffs((int)hm) - 1);
-                if (handoff) io.handoff[1 + base + __popc(hm & ((1u << lane) - 1u))] = idx;
+                if (handoff) {
+                    io.handoff[1 + base + __popc(hm & ((1u << lane) - 1u))] = idx;
+                    if constexpr (ROLLOUT) { // the episode so far (its board of this step's start is already in HBM)
+                        ro.total_reward[idx] = total;
+                        ro.steps_done[idx] = steps_done;
+                        if (ro.status) ro.status[idx] = (uint8_t)st_acc;
+                    }
+                }
             }
         }
     }
@@ -837,10 +853,29 @@ int op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaS
     }
     return 1;
 }
-void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left, long long *total_reward,
-                int32_t *steps_done, uint8_t *status, int types, long long n, cudaStream_t s) {
+// Philox rollouts with a work list: the common-case kernel plays the episodes; an episode that meets a rare case is
+// parked (board of the step's start, reward and step count so far) and finished by the exact kernel
+template <class SH>
+void launch_two_kernel_rollout(RefillDev rf, RolloutDev ro, int32_t *handoff, int types, long long n, cudaStream_t s) {
+    cudaMemsetAsync(handoff, 0, sizeof(int32_t), s);
+    StepDev io = {};
+    io.handoff = handoff;
+    launch_lanes<SH, true, true, true>(rf, io, ro, types, n, s);
+    StepDev io2 = {};
+    io2.jobs = handoff + 1;
+    io2.n_jobs = handoff;
+    launch_lanes<SH, true, true, false>(rf, io2, ro, types, n, s);
+}
+
+int op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_t *moves_left, long long *total_reward,
+               int32_t *steps_done, uint8_t *status, int32_t *scratch, int types, long long n, cudaStream_t s) {
     const StepDev io = {};
     const RolloutDev ro = {boards, moves_left, total_reward, steps_done, status};
+    if (philox && scratch && steps_done && n <= (1ll << 29)) {
+        if (wide) launch_two_kernel_rollout<SHW>(rf, ro, scratch, types, n, s);
+        else launch_two_kernel_rollout<SHN>(rf, ro, scratch, types, n, s);
+        return 2;
+    }
     if (wide) {
         if (philox) launch_lanes<SHW, true, true>(rf, io, ro, types, n, s);
         else launch_lanes<SHW, false, true>(rf, io, ro, types, n, s);
@@ -848,6 +883,7 @@ void op_rollout(bool wide, bool philox, RefillDev rf, void *boards, const int32_
         if (philox) launch_lanes<SHN, true, true>(rf, io, ro, types, n, s);
         else launch_lanes<SHN, false, true>(rf, io, ro, types, n, s);
     }
+    return 1;
 }
 
 void op_onehot(const void *boards, void *out, int channels, int elem_kind, int types, long long n, cudaStream_t s) {

@@ -100,6 +100,7 @@ class _LeafBuffers:
         self.moves_left = torch.zeros(count, dtype=torch.int32, device=device)
         self.total = torch.zeros(count, dtype=torch.int64, device=device)
         self.steps = torch.zeros(count, dtype=torch.int32, device=device)
+        self.scratch = torch.empty(count + 1, dtype=torch.int32, device=device)  # work list of the two-kernel rollout
 
 
 def replicate(state: BoardV2, n: int, *, key: int, board0: int, device=None) -> BatchedBoards:
@@ -171,8 +172,9 @@ class BatchedRolloutMCTS:
             lb.moves_left.fill_(state.n_actions)
             rf = N.Refill()
             rf.mode, rf.philox_key, rf.board0, rf.step_ctr = N.REFILL_PHILOX, self.key, sim * self.leaves + first, 0
-            N.check(N.lib().ecg_rollout(C.byref(nat), C.byref(rf), _ptr(lb.boards), _ptr(lb.moves_left), _ptr(lb.total),
-                                        _ptr(lb.steps), None, count, _stream(dev)), "ecg_rollout")
+            N.check(N.lib().ecg_rollout_scratch(C.byref(nat), C.byref(rf), _ptr(lb.boards), _ptr(lb.moves_left),
+                                                _ptr(lb.total), _ptr(lb.steps), None, _ptr(lb.scratch), count,
+                                                _stream(dev)), "ecg_rollout")
             rsum = lb.total.sum() + int(state.reward) * count
             steps = lb.steps.sum().to(torch.int64)
         else:
@@ -183,9 +185,9 @@ class BatchedRolloutMCTS:
                 picks = torch.zeros(n, dtype=torch.int64, device=dev)
                 picks[int(np.random.RandomState(state.cfg.seed).choice(n))] = count
             else:  # the reference seeds this pick from Python's `random`: uniform over the legal set
-                g = torch.Generator(device="cpu")
-                g.manual_seed((self.key * 1000003 + sim * 8191 + rank) & (2 ** 63 - 1))
-                picks = torch.bincount(torch.randint(n, (count,), generator=g), minlength=n).to(dev)
+                import numpy as np
+                g = np.random.Generator(np.random.PCG64((self.key * 1000003 + sim * 8191 + rank) & (2 ** 63 - 1)))
+                picks = torch.from_numpy(g.multinomial(count, [1.0 / n] * n).astype(np.int64)).to(dev)
             rsum = (picks * returns).sum()
         # one reduction, one device-to-host read per simulation: (reward sum, env-steps); visits are known on the host
         both = torch.stack([rsum.to(torch.int64).reshape(()), steps.reshape(())])

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ECG_VERSION 104
+#define ECG_VERSION 105
 
 /* per-board status bits */
 #define ECG_ST_TERMINAL 1        /* n_actions < 1: board returned unchanged (boardv2.py:44-45) */
@@ -177,6 +177,13 @@ int ecg_step_mark_event(void *event);
  * collected; steps_done (optional, [n]) the number of actions applied. */
 int ecg_rollout(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
                 int64_t *total_reward, int32_t *steps_done, uint8_t *status, int64_t n, void *stream);
+/* The same with a work list (scratch: [n + 1] int32, contents irrelevant on entry and exit; needs steps_done).  Philox
+ * mode: the episodes are played by the common-case kernel; an episode that meets a rare case (see ecg_step_io.scratch)
+ * is parked -- the board of that step's start, the reward and step count so far -- and finished by the exact kernel.
+ * Results are identical with and without the list. */
+int ecg_rollout_scratch(const ecg_config *cfg, const ecg_refill *rf, void *boards, const int32_t *moves_left,
+                        int64_t *total_reward, int32_t *steps_done, uint8_t *status, int32_t *scratch, int64_t n,
+                        void *stream);
 
 /* Observation for the policy/value net: nnx.one_hot(board.array, channels) (elementCrush.py:66,92), layout
  * [n, rows, cols, channels]; a cell value >= channels (e.g. the mega token, 32 of 32 channels) is all zeros, as in

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(E):
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(E._native.EXPORTS), declared ^ set(E._native.EXPORTS)
-    assert E._native.lib().ecg_version() == 104
+    assert E._native.lib().ecg_version() == 105
 
 
 def test_struct_layouts_match_header(E):

@@ -117,7 +117,7 @@ def test_replay_rollouts_reproduce_reference_dynamics(E):
         cfg = E.BoardConfig(seed=seed)
         state = E.BoardV2(moves, cfg)
         m = E.BatchedRolloutMCTS(state, 3, 1, False, deterministic=True, leaves=8, refill="replay")
-        returns = m._first_action_returns(state).cpu().numpy()
+        returns = m._first_action_returns(state)[0].cpu().numpy()
         legal = state.legal_actions
         assert len(returns) == len(legal)
         golden_total = int(d["rewards"][e].sum())
@@ -128,7 +128,7 @@ def test_replay_rollouts_reproduce_reference_dynamics(E):
         assert (rsum, n) == (8 * golden_total, 8)
         # a deeper state with points already collected: the return includes state.reward
         s2 = state.apply_action(int(d["actions"][e, 0])).apply_action(int(d["actions"][e, 1]))
-        r2 = m._first_action_returns(s2).cpu().numpy()
+        r2 = m._first_action_returns(s2)[0].cpu().numpy()
         assert r2[s2.legal_actions.index(int(d["actions"][e, 2]))] == golden_total
         # non-deterministic: first picks uniform over the legal set, sums reproducible from (key, simulation)
         m2 = E.BatchedRolloutMCTS(state, 3, 1, False, leaves=4096, key=9, refill="replay")
