@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (weak) / in total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-chunks", type=int, default=32, help="HostStepper chunks (copy / kernel pipeline depth)")
     ap.add_argument("--sustained-seconds", type=float, default=5.0)
     ap.add_argument("--replay-steps", type=int, default=12)
     ap.add_argument("--sweep-boards", type=int, default=1 << 22, help="boards per GPU and shape of the shape sweep")
@@ -313,7 +314,7 @@ def run_ours(args):
 
     # ---- e2e through the host-buffer API: the env contract (uint8 cells) and the 4-bit form
     def e2e_leg(fmt):
-        hs = E.HostStepper(env, chunks=8, obs_format=fmt)
+        hs = E.HostStepper(env, chunks=args.e2e_chunks, obs_format=fmt)
         for _ in range(2):
             hs.step(hs.random_action())
         torch.cuda.synchronize(dev)
@@ -332,7 +333,7 @@ def run_ours(args):
                "pcie_d2h_gb_s_per_gpu": d2h * args.e2e_steps / dt / 1e9,
                "pcie_d2h_gb_s_all_gpus": sum_over_ranks(d2h) * args.e2e_steps / dt / 1e9,
                "api": "HostStepper.random_action() + HostStepper.step(actions_host) -> (obs, reward, done, won) in "
-                      "pinned host memory, 8 chunks pipelined over CUDA streams; obs = " +
+                      f"pinned host memory, {args.e2e_chunks} chunks pipelined over CUDA streams; obs = " +
                       ("uint8 [N,9,9] cell values, int32 reward/actions (the env contract)" if fmt == "uint8" else
                        "uint8 [N,41] 4-bit cell codes (ecg_unpack_nibbles), int16 reward/actions")}
         del hs

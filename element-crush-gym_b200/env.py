@@ -91,7 +91,8 @@ class BatchedMatch3Env:
 class HostStepper:
     """The public call with HOST buffers: actions come from pinned host memory, observation, reward, done
     and won go back to pinned host memory every step.  The batch is cut into chunks whose H2D copy, step
-    kernel and D2H copies run on separate CUDA streams so PCIe transfers overlap the kernels.
+    kernel and D2H copies run on separate CUDA streams so PCIe transfers overlap the kernels (2^24 boards: 5.2e8 /
+    5.6e8 / 5.8e8 env-steps/s with 2 / 8 / 32 chunks, 8.4e8 / 9.3e8 / 1.07e9 with the 4-bit observation, r06).
     bench.py's e2e number is measured through this class.
 
     obs_format="uint8" (default, the env contract): observation uint8 [N, H, W] of cell VALUES, reward int32,
@@ -101,7 +102,7 @@ class HostStepper:
         (ecg_unpack_nibbles; `decode_obs` turns it into the uint8 form on the host when wanted), reward int16
         (saturating), actions int16."""
 
-    def __init__(self, env: BatchedMatch3Env, chunks: int = 8, obs_format: str = "uint8"):
+    def __init__(self, env: BatchedMatch3Env, chunks: int = 16, obs_format: str = "uint8"):
         if obs_format not in ("uint8", "nibbles"):
             raise ValueError("obs_format must be 'uint8' or 'nibbles'")
         self.env = env
