@@ -438,8 +438,17 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_rate(12.0)
-        cpu["python_reference"] = ("absent on this box: the reference is pure Python under /root/reference of the "
-                                   "authoring container and cannot travel; measured there: see BASELINE.md / DESIGN.md")
+        try:  # the reference's own Python/NumPy path: measured where it can be imported, committed as a file
+            with open(os.path.join(ROOT, "profiles", "python_reference_authoring_container.json")) as f:
+                pr = json.load(f)
+            cpu["python_reference"] = {
+                "where": "NOT this box: the reference is pure Python under /root/reference of the authoring container "
+                         "and cannot travel; scripts/time_python_reference.py ran it there",
+                "cpu": pr["cpu"], "cores": pr["cores"],
+                "single_process_env_steps_per_s": pr["single_process"]["env_steps_per_s"],
+                "all_cores_reference_pool_env_steps_per_s": pr["all_cores_reference_pool"]["env_steps_per_s"]}
+        except Exception:
+            cpu["python_reference"] = "absent on this box (pure Python, cannot travel)"
 
     if rank == 0:
         peak, peak_src = measured_peak()

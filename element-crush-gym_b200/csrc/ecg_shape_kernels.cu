@@ -486,13 +486,13 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
     if constexpr (!FAST)
         if (io.n_jobs) n = *io.n_jobs;
     const int lane = threadIdx.x & 31;
-    const int warp = (int)((blockIdx.x * lane_block(FAST) + threadIdx.x) >> 5);
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // (blockDim.x <= lane_block(FAST))
     // The hand-off list of a two-kernel step is short (0.6 % of the boards: 94 k jobs for 2 368 warps): every warp takes
     // ONE contiguous range of (almost) the same length.  Chunks of 32 handed round-robin left some warps with 64 jobs and
     // others with 32 (6.98e9 env-steps/s at 9x9x6; chunks of 16: 7.11e9; equal ranges: 7.18e9).
-    const int nwarps_all = (int)((gridDim.x * lane_block(FAST)) >> 5);
+    const int nwarps_all = (int)((gridDim.x * blockDim.x) >> 5);
     const int CHUNK = (!FAST && io.n_jobs) ? (n + nwarps_all - 1) / nwarps_all + (n == 0) : ::CHUNK_BOARDS;
-    const int stride = (int)((gridDim.x * lane_block(FAST)) >> 5) * CHUNK; // host guarantees n + stride + CHUNK < 2^31
+    const int stride = nwarps_all * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
     int chunk0 = warp * CHUNK;
     int next = chunk0 < n ? chunk0 : n;
@@ -817,6 +817,28 @@ void launch_lanes(RefillDev rf, StepDev io, RolloutDev ro, int types, long long 
         <<<persistent_grid(lane_kernel<SH, PHILOX, ROLLOUT, FAST>, n, B), B, 0, s>>>(rf, io, ro, types, (int)n);
 }
 
+// The exact kernel over the hand-off list of a two-kernel STEP.  The list is short (0.6 % of the boards) and its boards
+// cascade long (4 iterations on average against 1.5): with all 16 warps per SM every warp got 40 jobs for its 32 lanes,
+// ran to its slowest lane (7.6 trips at 17 active lanes) and shared the issue slots with 15 others.  Fewer, smaller
+// blocks give every warp more jobs to refill its lanes with and faster trips.
+#ifndef ECG_JOBS_BLOCK
+#define ECG_JOBS_BLOCK lane_block(false)
+#endif
+#ifndef ECG_JOBS_PER_SM
+#define ECG_JOBS_PER_SM 1
+#endif
+template <class SH, bool PHILOX>
+void launch_jobs(RefillDev rf, StepDev io, int types, long long n, cudaStream_t s) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const RolloutDev ro = {};
+    lane_kernel<SH, PHILOX, false, false><<<sms * ECG_JOBS_PER_SM, ECG_JOBS_BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
+}
+
 // The two-kernel step (Philox mode, or replay mode with tile tables): the common-case kernel over all boards, then the
 // exact kernel over the jobs it handed off (their number is read on the device: no host synchronisation in between)
 template <class SH, bool PHILOX>
@@ -829,7 +851,7 @@ void launch_two_kernel_step(RefillDev rf, StepDev io, long long n, cudaStream_t 
     io2.jobs = io.handoff + 1;
     io2.n_jobs = io.handoff;
     io2.handoff = nullptr;
-    launch_lanes<SH, PHILOX, false, false>(rf, io2, ro, io.types, n, s);
+    launch_jobs<SH, PHILOX>(rf, io2, io.types, n, s);
 }
 
 int op_step(bool wide, bool philox, RefillDev rf, StepDev io, long long n, cudaStream_t s) {
