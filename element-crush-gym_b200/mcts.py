@@ -134,7 +134,7 @@ class BatchedRolloutMCTS:
         self._leaf = None   # _LeafBuffers of this rank
         self._root.expand()  # abc/mcts.py:82
 
-    def _first_action_returns(self, state: BoardV2) -> torch.Tensor:
+    def _first_action_returns(self, state: BoardV2):
         """refill="replay": final cumulative reward of the reference's rollout for every legal first action of
         `state`, int64 [L] on the device (standard/mcts.py:16-18 over boardv2.py:46), and the env-steps simulated."""
         legal = state.legal_actions
@@ -178,7 +178,9 @@ class BatchedRolloutMCTS:
             rsum = lb.total.sum() + int(state.reward) * count
             steps = lb.steps.sum().to(torch.int64)
         else:
-            returns, steps = self._first_action_returns(state)  # [L]
+            returns, steps = self._first_action_returns(state)  # [L]; every rank plays the same few episodes
+            if rank:
+                steps = torch.zeros_like(steps)  # counted once
             n = returns.numel()
             if self.deterministic:  # np.random.seed(cfg.seed); np.random.choice(legal): one fixed first pick
                 import numpy as np
