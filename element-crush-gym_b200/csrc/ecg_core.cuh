@@ -1223,16 +1223,15 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
 #endif
     } else if constexpr (UsesTileWindow<RNG>::value) {
         // the reference's order with precomputed tiles (ReplayTileRng): 16 tiles per window, one nibble per hole.
+        // ONE flat loop, one hole per trip, the next hole chosen without a branch (down the column, else the top of
+        // the next column with a hole): as nested column / hole loops the lanes of a warp waited for each other at
+        // every column change (24 trips per warp iteration at 5 of 32 lanes, ncu r04c / r04d).
         uint32_t cols = holes.w[0] & ((1u << G::C) - 1u); // holes are top-aligned after gravity
-        const int total = popcount(holes);
-        if (total > 16) {
-            // more tiles than one window holds (rare: lines and bombs): ONE flat loop, one hole per trip, the next
-            // hole chosen without a branch (down the column, else the top of the next column with a hole) -- as nested
-            // column / hole loops the lanes of a warp waited for each other at every column change (ncu r04c / r04d)
+        if (cols) {
             uint32_t t = rng.tpos;
             int bit = ctz32(cols);
             bool more = true;
-            do {
+            do { // one window of 16 tiles per pass: a second pass is rare
                 uint32_t lo, hi;
                 rng.window(t, lo, hi);
                 t += 16u;
@@ -1258,48 +1257,7 @@ ECG_PHASE void refill(Board<typename SH::G> &b, RNG &rng, uint32_t types, int it
                     bit = down ? nb : ctz32(rest | 0x80000000u);
                 } while (more && --left);
             } while (more);
-        } else if (total) {
-            // one window is enough.  One loop trip per COLUMN with a hole: its first DR rows lie in word 0 whatever the
-            // column (static word, the row bits one shift apart), so their tiles are deposited under predicates without
-            // a dynamic word index; deeper holes of the column (rare) follow in a short loop before the next column.
-            // 7 trips of ~36 instructions per warp iteration instead of 12.5 trips of 47 (ncu r06).
-            constexpr int DR = 32 / G::S < G::R ? 32 / G::S : G::R; // rows 0 .. DR-1 sit entirely in word 0
-            uint32_t lo, hi;
-            rng.window(rng.tpos, lo, hi);
-            do {
-                const int c = ctz32(cols);
-                cols &= cols - 1u;
-                const uint32_t mc = 1u << c;
-#pragma unroll
-                for (int r = 0; r < DR; r++) {
-                    const uint32_t m = mc << (r * G::S);
-                    if (r == 0 || (holes.w[0] & m)) {
-                        deposit_bit<1>(b.p[0].w[0], lo, m);
-                        deposit_bit<2>(b.p[1].w[0], lo, m);
-                        deposit_bit<4>(b.p[2].w[0], lo, m);
-                        if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[0], lo, m);
-                        lo = funnel_r(lo, hi, 4);
-                        hi >>= 4;
-                    }
-                }
-                for (int bit = c + DR * G::S; testbit(holes, bit); bit += G::S) { // (bits past the board are never set)
-                    const int wi = bit >> 5;
-                    const uint32_t m = 1u << (bit & 31);
-#pragma unroll
-                    for (int i = 0; i < G::W; i++) {
-                        const uint32_t mi = (i == wi) ? m : 0u;
-                        deposit_bit<1>(b.p[0].w[i], lo, mi);
-                        deposit_bit<2>(b.p[1].w[i], lo, mi);
-                        deposit_bit<4>(b.p[2].w[i], lo, mi);
-                        if (SH::TPL > 3) deposit_bit<8>(b.p[3].w[i], lo, mi);
-                    }
-                    lo = funnel_r(lo, hi, 4);
-                    hi >>= 4;
-                }
-            } while (cols);
-        }
-        if (total) {
-            rng.tpos += (uint32_t)total;
+            rng.tpos += (uint32_t)popcount(holes);
             rng.check_end();
         }
     } else {
