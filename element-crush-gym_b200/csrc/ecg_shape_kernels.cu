@@ -491,7 +491,12 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
     // ONE contiguous range of (almost) the same length.  Chunks of 32 handed round-robin left some warps with 64 jobs and
     // others with 32 (6.98e9 env-steps/s at 9x9x6; chunks of 16: 7.11e9; equal ranges: 7.18e9).
     const int nwarps_all = (int)((gridDim.x * blockDim.x) >> 5);
-    const int CHUNK = (!FAST && io.n_jobs) ? (n + nwarps_all - 1) / nwarps_all + (n == 0) : ::CHUNK_BOARDS;
+    // Chunks of CHUNK_BOARDS boards -- smaller (down to one tile) when the batch is small, so that every warp still gets
+    // eight of them: with fixed 256-board chunks a batch of 2^17 boards filled 32 of the 148 SMs and one of 2^21 left
+    // a quarter of the warps idle for the last chunk.
+    int chunk = ::CHUNK_BOARDS;
+    while (chunk > 32 && (long long)n < (long long)nwarps_all * chunk * 8) chunk >>= 1;
+    const int CHUNK = (!FAST && io.n_jobs) ? (n + nwarps_all - 1) / nwarps_all + (n == 0) : chunk;
     const int stride = nwarps_all * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
     int chunk0 = warp * CHUNK;
@@ -805,7 +810,7 @@ unsigned persistent_grid(K kernel, long long n, int block) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const long long chunks = (n + CHUNK_BOARDS - 1) / CHUNK_BOARDS;
+    const long long chunks = (n + 31) / 32; // the kernel shrinks its chunks down to one tile for small batches
     const long long blocks = (chunks + (block / 32) - 1) / (block / 32);
     return (unsigned)(blocks < resident ? blocks : resident);
 }
