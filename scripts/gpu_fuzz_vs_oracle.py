@@ -38,11 +38,6 @@ for rows, types in SHAPES:
     mism = 0
     for t in range(moves):
         bb.apply_action(None)
-        a = np_(bb.last_actions)
-        ok = a >= 0
-        res = o.step_batch(boards[ok], a[ok], mode="philox", key=KEY, board0=0, step_ctr=t) if False else None
-        # (board ids differ per board: step the boards one id at a time through the episode API below instead)
-        boards = np_(bb.array)
     final, total, steps = o.philox_episode_batch(np_(roll.array), KEY, 1000, moves)
     mism += int((np_(bb.array) != final).any(axis=(1, 2)).sum()) + int((np_(bb.reward) != total).sum())
     tot = roll.rollout()
@@ -52,8 +47,8 @@ for rows, types in SHAPES:
     total_steps += 2 * int(steps.sum())
     # ---- replay: per-board MT19937 streams, every step against step_batch
     seeds = np.arange(1, nn // 8 + 1, dtype=np.int64)
-    rb = E.BatchedBoards(cfg, len(seeds), moves, refill="replay", seeds=seeds, stream_len=2048)
-    raw = np.stack([Oracle.mt_raw(int(s), 2048) for s in seeds])
+    rb = E.BatchedBoards(cfg, len(seeds), moves, refill="replay", seeds=seeds, stream_len=4096)
+    raw = np.stack([Oracle.mt_raw(int(s), 4096) for s in seeds])
     rboards = np_(rb.array)
     rr = rb.clone()
     rm = 0
@@ -62,7 +57,10 @@ for rows, types in SHAPES:
         a = np_(rb.last_actions)
         res = o.step_batch(rboards, a, mode="replay", raw=raw)
         rm += int((np_(rb.array) != res["boards"]).any(axis=(1, 2)).sum()) + int((np_(rb.step_reward) != res["reward"]).sum())
-        rm += int((np_(rb.cascades) != res["cascades"]).sum()) + int((np_(rb.status) != res["status"]).sum())
+        # a board without a legal move is a no-op on both sides; the engine says NO_LEGAL, the oracle (handed action
+        # -1) BAD_ACTION
+        want_status = np.where(a < 0, E.ST_NO_LEGAL, res["status"])
+        rm += int((np_(rb.cascades) != res["cascades"]).sum()) + int((np_(rb.status) != want_status).sum())
         rm += int((np_(rb.legal_mask()) != res["legal"]).any(axis=1).sum())
         rboards = res["boards"]
         total_steps += len(seeds)
