@@ -47,8 +47,12 @@ for rows, types in SHAPES:
     total_steps += 2 * int(steps.sum())
     # ---- replay: per-board MT19937 streams, every step against step_batch
     seeds = np.arange(1, nn // 8 + 1, dtype=np.int64)
-    rb = E.BatchedBoards(cfg, len(seeds), moves, refill="replay", seeds=seeds, stream_len=4096)
-    raw = np.stack([Oracle.mt_raw(int(s), 4096) for s in seeds])
+    # few types cascade for hundreds of iterations: a stream that runs out makes the NEXT pick overflow on the engine's
+    # side only (the oracle is handed the action), so give those shapes streams that never run out
+    sl = 32768 if types <= 3 else 4096
+    seeds = seeds[: len(seeds) // (4 if types <= 3 else 1)]
+    rb = E.BatchedBoards(cfg, len(seeds), moves, refill="replay", seeds=seeds, stream_len=sl)
+    raw = np.stack([Oracle.mt_raw(int(s), sl) for s in seeds])
     rboards = np_(rb.array)
     rr = rb.clone()
     rm = 0
