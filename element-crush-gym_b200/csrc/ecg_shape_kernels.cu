@@ -397,6 +397,9 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(RefillDev rf, void *boards,
 #define ECG_CHUNK 256
 #endif
 constexpr int CHUNK_BOARDS = ECG_CHUNK;
+#ifndef ECG_MIN_CHUNKS
+#define ECG_MIN_CHUNKS 8 // chunks every warp should get before the chunk size stops shrinking (16 / 32 / 64: no gain, r08)
+#endif
 // The lane kernel runs ONE block of LANE_BLOCK threads per SM whose warps walk the trip loop together (one
 // __syncthreads_or per trip).  The loop body is ~35 KB of SASS, more than the SM's 32 KB instruction cache; 16
 // free-running warps each streamed it on their own (stall_no_inst 56 % of stall samples, GPC instruction-fetch path
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
     // eight of them: with fixed 256-board chunks a batch of 2^17 boards filled 32 of the 148 SMs and one of 2^21 left
     // a quarter of the warps idle for the last chunk.
     int chunk = ::CHUNK_BOARDS;
-    while (chunk > 32 && (long long)n < (long long)nwarps_all * chunk * 8) chunk >>= 1;
+    while (chunk > 32 && (long long)n < (long long)nwarps_all * chunk * ECG_MIN_CHUNKS) chunk >>= 1;
     const int CHUNK = (!FAST && io.n_jobs) ? (n + nwarps_all - 1) / nwarps_all + (n == 0) : chunk;
     const int stride = nwarps_all * CHUNK; // host guarantees n + stride + CHUNK < 2^31
     // warp-uniform cursor over this warp's chunks
