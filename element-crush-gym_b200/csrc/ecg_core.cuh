@@ -1096,6 +1096,9 @@ ECG_HD BB<SH::G::W> trigger_specials(const Board<typename SH::G> &bd, const BB<S
 template <class G>
 ECG_PHASE void gravity(Board<G> &b) {
     constexpr int W = G::W, S = G::S;
+#if defined(ECG_SIM_HOOKS) && !defined(__CUDA_ARCH__) // host experiments only (scripts/experiments): found by ADL
+    ecg_sim_gravity_hook(b);
+#endif
     for (;;) {
         const BB<W> occ = b.p[0] | b.p[1] | b.p[2] | b.p[3];
         const BB<W> holes = andn(G::valid(), occ);
