@@ -8,6 +8,7 @@ Host-side mirror of the reference interface for the hot path only:
     dist                              sharding + NCCL reduction of statistics
     BatchedRolloutMCTS                mctslib/standard/mcts.py with GPU-batched rollouts
     dataset / Dataset                 dataset.py (self-play samples, mirror / type-switch augmentation)
+    sampler                           samplerTasks.py + util/multiprocessingAutoBatcher.py (episodes sharded over ranks)
 All board logic runs in libecg.so (hand-written CUDA for sm_100a behind include/ecg.h); there is no CPU path.
 The directory name is not a Python identifier: import it with
     importlib.import_module("element-crush-gym_b200")      # or `import ecg_b200` (alias module at the repo root)
@@ -23,6 +24,7 @@ from . import dist
 from .mcts import BatchedRolloutMCTS
 from . import dataset
 from .dataset import Dataset
+from . import sampler
 
 __all__ = ["BoardConfig", "BoardV2", "BatchedBoards", "BatchedMatch3Env", "Match3Env", "HostStepper", "dist",
-           "EcgError", "fresh_key", "BatchedRolloutMCTS", "dataset", "Dataset"]
+           "EcgError", "fresh_key", "BatchedRolloutMCTS", "dataset", "Dataset", "sampler"]
