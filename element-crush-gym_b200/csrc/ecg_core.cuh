@@ -1456,7 +1456,10 @@ ECG_HD void step_begin(Lane<SH> &L, int action) {
 // final board (the reference computes legal_actions there too, :188, to decide about shuffling).
 // FAST = true (see find_matches): `rare` is set (and false returned) when the iteration needs the exact build:
 // a rare match case, or a final board without a legal swap (the shuffle loop).
-template <class SH, class RNG, bool FAST>
+// DEFER_LEGAL = true (the pooled step kernel): when the cascade ends, HL / VL are left alone; the caller computes the
+// legal swaps of the final board later, when a full warp of finished boards has gathered (and hands the board over
+// itself if none is legal).
+template <class SH, class RNG, bool FAST, bool DEFER_LEGAL = false>
 ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, BB<SH::G::W> &VL, bool &rare) {
     using G = typename SH::G;
     constexpr int W = G::W;
@@ -1492,6 +1495,18 @@ ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, B
         return false;
     }
     bool done = false;
+    if constexpr (DEFER_LEGAL) {
+        if (!m.found) return true;
+        L.cleared = m.mask;
+        L.sp = m.sp;
+        L.sk0 = m.sk0;
+        L.sk1 = m.sk1;
+        if (rng.overflow || L.cascades >= CASCADE_CAP) { // the pending match stays unapplied, like below
+            L.status |= rng.overflow ? ST_STREAM_OVERFLOW : ST_CASCADE_CAP;
+            return true;
+        }
+        return false;
+    }
     if (!m.found) {
         legal_swaps<SH>(d, m.A, m.D, HL, VL);
         if (FAST && !any(HL | VL)) {
@@ -1532,6 +1547,19 @@ ECG_HD bool step_iter(Lane<SH> &L, RNG &rng, uint32_t types, BB<SH::G::W> &HL, B
     }
     if (done && rng.overflow) L.status |= ST_STREAM_OVERFLOW;
     return done;
+}
+
+// What the coming cascade iteration of a lane will cost, from its pending match (the pooled step kernel runs lanes
+// of one class together, so the gravity / refill loops of a warp end together): 0 = one horizontal run of three on a
+// board without special tokens (three holes in one row: one gravity move, three tiles), 1 = one vertical run of three
+// (up to three moves, three tiles), 2 = everything else.
+constexpr int CASCADE_CLASSES = 3;
+template <class SH>
+ECG_HD int cascade_class(const Lane<SH> &L) {
+    using G = typename SH::G;
+    const bool plain3 = popcount(L.cleared) == 3 && !any((L.bd.p[3] & L.bd.p[2]) | L.sp);
+    if (!plain3) return 2;
+    return any(L.cleared & shl<G::S>(L.cleared)) ? 1 : 0;
 }
 
 template <class SH, class RNG>
