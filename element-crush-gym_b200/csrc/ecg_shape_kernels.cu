@@ -10,6 +10,7 @@
 // moves a whole tile with CH fully coalesced 512-byte LDG.128/STG.128 transactions.
 // Legal masks use the same tiling with 4-byte words: u32 index (tile*MW + w)*32 + lane.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/ecg.h"
 #include "ecg_core.cuh"
@@ -746,94 +747,93 @@ __global__ void __launch_bounds__(lane_block(FAST), ECG_LANE_MINB) lane_kernel(R
 //
 // The lane kernel above keeps one board per lane for its whole step; lanes of a warp are in different phases (65 % of
 // them finish their cascade in a trip), so FINISH / FETCH / BEGIN ran at 20 of 32 lanes and the gravity / refill loops
-// to the warp's worst board (ncu r09: 18 of 32 threads per instruction).  Here a warp owns a POOL of boards in shared
-// memory (POOL_SLOTS slots, word w of slot s at pool[w * POOL_SLOTS + s]) and runs ONE phase per pass on up to 32 of
-// them, all lanes together:
-//   BEGIN   one 32-board tile from HBM: action pick, swap, first match pass -> slot, listed by cascade_class
-//   ITERATE 32 slots of ONE class: one cascade iteration in place -> listed by its new class, or as finished
-//   FINISH  32 finished slots: legal swaps of the final board, outputs to HBM, slot freed
-// Lists of slot numbers (bytes) per class / finished / free; all of it is private to the warp: no barriers, no atomics
-// (except the hand-off list of the two-kernel step, as before).  Philox lockstep steps without src_index only.
+// to the warp's worst board (ncu r09: 18 of 32 threads per instruction).  Here a BLOCK owns a pool of boards in shared
+// memory (PoolGeo::SLOTS slots, word w of slot s at pool[w * SLOTS + s]) and runs ONE phase per pass on POOL_BLOCK of
+// them, all threads together:
+//   BEGIN   POOL_BLOCK boards from HBM: action pick, swap, first match pass -> slot, listed by cascade_class
+//   ITERATE POOL_BLOCK slots of ONE class: one cascade iteration in place -> listed by its new class, or as finished
+//   FINISH  POOL_BLOCK finished slots: legal swaps of the final board, outputs to HBM, slot freed
+// Lists of slot numbers per class / finished / free, appended to with one shared-memory atomic per warp and list; two
+// barriers per pass (lists merged and read | slots processed and listed).  All warps of a block run the same phase, so
+// the instruction cache holds one phase at a time (warp-private pools were measured first, profiles/r10_warp_pool_*:
+// 16 warps in three different phases stream 54 KB of SASS, i-cache hit 81 %).  Philox lockstep steps without
+// src_index only; batches too small to keep every block's pool busy stay with the lane kernel.
+//
+// MEASURED AND REJECTED (round 2, profiles/r10_block_pool_*): bit-exact, but 2.64 ms per 2^24-board launch against the
+// lane kernel's 2.15 ms.  The phases shrink as planned (BEGIN 830 -> 650, FINISH 475 -> 374 warp-instructions per 32
+// boards at 32 of 32 lanes, gravity loop 390 -> 290, refill loops 290 -> 145), but moving the 28-word lane states
+// through shared memory every pass, the lists, the per-pass decision and the class test cost ~630, and the issue rate
+// falls from 60 % to 41-50 % (the loads of a BEGIN pass are no longer hidden behind other lanes' cascades).  Compiled
+// only with -DECG_POOL=1 (scripts/build_variant.sh); tests/test_gpu_pool.py covers it when it is.
+#ifndef ECG_POOL
+#define ECG_POOL 0
+#endif
+#if ECG_POOL
 #ifndef ECG_POOL_BLOCK
-#define ECG_POOL_BLOCK 512
+#define ECG_POOL_BLOCK 64
 #endif
-#ifndef ECG_POOL_SMEM
-#define ECG_POOL_SMEM 232448 // 227 KB: the opt-in maximum of dynamic shared memory per block on sm_100
+#ifndef ECG_POOL_PER_SM
+#define ECG_POOL_PER_SM (512 / ECG_POOL_BLOCK)
 #endif
-constexpr int POOL_BLOCK = ECG_POOL_BLOCK;
+constexpr int POOL_BLOCK = ECG_POOL_BLOCK, POOL_PER_SM = ECG_POOL_PER_SM;
 constexpr int POOL_LISTS = CASCADE_CLASSES + 2; // classes, finished, free
+constexpr int POOL_HDR = 64;                    // two sets of list-growth counters
 template <class SH>
 struct PoolGeo {
     static constexpr int W = SH::G::W;
     static constexpr int SLOT_WORDS = 8 * W + 4; // board 4W, cleared / sp / sk0 / sk1 W each, idx, action, reward, cascades | status
-    static constexpr int WARP_BYTES = (ECG_POOL_SMEM / (POOL_BLOCK / 32)) & ~15;
-    static constexpr int raw = WARP_BYTES / (4 * SLOT_WORDS + POOL_LISTS);
-    static constexpr int SLOTS = (raw > 252 ? 252 : raw) & ~3; // slot numbers are bytes
-    static constexpr bool OK = SLOTS >= 96;
+    // 228 KB of shared memory per SM, 1 KB per block reserved, at most 227 KB per block
+    static constexpr int per_block = (233472 / POOL_PER_SM - 1024) & ~15;
+    static constexpr int BLOCK_BYTES = per_block > 232448 ? 232448 : per_block;
+    static constexpr int SLOTS = ((BLOCK_BYTES - POOL_HDR) / (4 * SLOT_WORDS + 2 * POOL_LISTS)) & ~3;
+    static constexpr bool OK = SLOTS >= 3 * POOL_BLOCK && SLOTS < 65536;
 };
 
 template <class SH>
-__global__ void __launch_bounds__(POOL_BLOCK, 1) pool_step_kernel(RefillDev rf, StepDev io, int types, int n) {
+__global__ void __launch_bounds__(POOL_BLOCK, POOL_PER_SM) pool_step_kernel(RefillDev rf, StepDev io, int types, int n) {
     using G = typename SH::G;
     using PG = PoolGeo<SH>;
-    constexpr int W = G::W, NS = PG::SLOTS;
+    constexpr int W = G::W, NS = PG::SLOTS, KB = POOL_BLOCK;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int OTHER = CASCADE_CLASSES - 1, FIN = CASCADE_CLASSES, FREE = CASCADE_CLASSES + 1;
     extern __shared__ __align__(16) unsigned char pool_smem[];
-    const int lane = threadIdx.x & 31;
+    int *const delta = reinterpret_cast<int *>(pool_smem); // [2][8]
+    uint32_t *const pool = reinterpret_cast<uint32_t *>(pool_smem + POOL_HDR);
+    uint16_t *const lists = reinterpret_cast<uint16_t *>(pool + NS * PG::SLOT_WORDS);
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t *const pool = reinterpret_cast<uint32_t *>(pool_smem + (size_t)(threadIdx.x >> 5) * PG::WARP_BYTES);
-    uint8_t *const lists = reinterpret_cast<uint8_t *>(pool + NS * PG::SLOT_WORDS);
     // slot word offsets
     constexpr int O_BD = 0, O_CL = 4 * W, O_SP = 5 * W, O_K0 = 6 * W, O_K1 = 7 * W, O_IDX = 8 * W, O_ACT = O_IDX + 1,
                   O_REW = O_IDX + 2, O_CS = O_IDX + 3;
 
-    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int nwarps_all = (int)((gridDim.x * blockDim.x) >> 5);
-    int CHUNK = ::CHUNK_BOARDS;
-    while (CHUNK > 32 && (long long)n < (long long)nwarps_all * CHUNK * ECG_MIN_CHUNKS) CHUNK >>= 1;
-    const int stride = nwarps_all * CHUNK;
-    int chunk0 = warp * CHUNK;
-    int next = chunk0 < n ? chunk0 : n;
-    int end = chunk0 + CHUNK < n ? chunk0 + CHUNK : n;
+    int group = blockIdx.x; // boards [group * KB, (group + 1) * KB), then group += gridDim.x
+    const int groups = (n + KB - 1) / KB;
 
-    int cnt[POOL_LISTS]; // warp-uniform list lengths (registers: every index below is a compile-time constant)
+    int cnt[POOL_LISTS]; // list lengths, the same in every thread of the block
 #pragma unroll
     for (int c = 0; c < POOL_LISTS; c++) cnt[c] = 0;
-    for (int s = lane; s < NS; s += 32) lists[FREE * NS + s] = (uint8_t)s;
+    for (int s = tid; s < NS; s += KB) lists[FREE * NS + s] = (uint16_t)s;
     cnt[FREE] = NS;
-    __syncwarp();
-
-    auto push = [&](int dest, int id) { // dest < 0: nothing to list for this lane
-        __syncwarp(); // every lane has read its slot number: the lists may be overwritten
-#pragma unroll
-        for (int c = 0; c < POOL_LISTS; c++) {
-            const unsigned m = __ballot_sync(FULL, dest == c);
-            if (dest == c) lists[c * NS + cnt[c] + __popc(m & lt)] = (uint8_t)id;
-            cnt[c] += __popc(m);
-        }
-    };
-    auto hand_over = [&](bool h, int idx) { // append to the hand-off list of the two-kernel step
-        const unsigned hm = __ballot_sync(FULL, h);
-        if (hm) {
-            int base = 0;
-            if (lane == __ffs((int)hm) - 1) base = atomicAdd(io.handoff, __popc(hm));
-            base = __shfl_sync(FULL, base, __ffs((int)hm) - 1);
-            if (h) io.handoff[1 + base + __popc(hm & lt)] = idx;
-        }
-    };
+    if (tid < 16) delta[tid] = 0;
+    int cur = 0; // the counter set this pass appends with
 
     for (;;) {
-        // ---- which phase, on how many lanes (all warp-uniform)
-        int phase = -1, k = 32; // phase: 0 .. CLASSES-1 ITERATE that class, FIN, FREE = BEGIN
-        if (cnt[FIN] >= 32) {
+        __syncthreads(); // the previous pass is complete: its slots and list entries are written
+        {
+            const int *dl = delta + (cur ^ 1) * 8;
+#pragma unroll
+            for (int c = 0; c < POOL_LISTS; c++) cnt[c] += dl[c];
+        }
+        // ---- which phase, on how many slots (the same decision in every thread)
+        int phase = -1, k = KB; // phase: 0 .. CLASSES-1 ITERATE that class, FIN, FREE = BEGIN
+        if (cnt[FIN] >= KB) {
             phase = FIN;
         } else {
 #pragma unroll
             for (int c = 0; c < CASCADE_CLASSES; c++)
-                if (phase < 0 && cnt[c] >= 32) phase = c;
+                if (phase < 0 && cnt[c] >= KB) phase = c;
             if (phase < 0) {
-                if (next < end && cnt[FREE] >= 32) {
+                if (group < groups && cnt[FREE] >= KB) {
                     phase = FREE;
                 } else {
                     int best = 0;
@@ -848,87 +848,145 @@ __global__ void __launch_bounds__(POOL_BLOCK, 1) pool_step_kernel(RefillDev rf, 
                         phase = FIN;
                         best = cnt[FIN];
                     }
-                    k = best; // < 32
+                    k = best; // < KB
                 }
             }
         }
-
+        int idx = 0;
         if (phase == FREE) {
-            // ---- BEGIN: the next tile of this warp's chunk
-            const int base = next;
-            k = end - next < 32 ? end - next : 32;
-            next += k;
-            if (next >= end && chunk0 + stride < n) {
-                chunk0 += stride;
-                next = chunk0;
-                end = chunk0 + CHUNK < n ? chunk0 + CHUNK : n;
-            }
-            if (next + lane < end) { // the lines of the tile after this one
+            const int base = group * KB;
+            k = n - base < KB ? n - base : KB;
+            idx = base + tid;
+            group += gridDim.x;
+            if (group < groups) { // the lines of this block's next boards
                 constexpr int CH = G::W;
-                const int pf = next + lane;
+                const int pf = group * KB + tid;
                 const uint4 *bp = reinterpret_cast<const uint4 *>(io.boards_in) + (long long)(pf >> 5) * (CH * 32) + (pf & 31);
+                if (pf < n) {
 #pragma unroll
-                for (int q = 0; q < CH; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + q * 32));
+                    for (int q = 0; q < CH; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + q * 32));
+                }
             }
-            const int idx = base + lane;
-            int dest = -1, id = 0, action = -1;
-            bool handoff = false;
-            Lane<SH> L;
-            if (lane < k) {
-                BB<W> HL, VL;
+        }
+        // ---- take k entries off the phase's list
+        int have = 0;
+#pragma unroll
+        for (int c = 0; c < POOL_LISTS; c++)
+            if (phase == c) {
+                have = cnt[c];
+                cnt[c] -= k;
+            }
+        const bool on = tid < k;
+        const int id = on ? (int)lists[phase * NS + have - k + tid] : 0;
+        uint32_t *const sl = pool + id;
+        __syncthreads(); // every thread has read the lists: this pass may append to them
+        if (tid < 8) delta[(cur ^ 1) * 8 + tid] = 0;
+
+        Lane<SH> L;
+        BB<W> HL, VL;
+        int dest = -1, action = -1, moves = 0;
+        bool handoff = false;
+        uint32_t st = 0;
+        if (on) {
+            if (phase == FREE) { // FETCH
                 load_board<G>(io.boards_in, idx, L.bd);
-                int moves = io.moves_left ? io.moves_left[idx] : 1;
+                moves = io.moves_left ? io.moves_left[idx] : 1;
                 if (!io.actions) load_mask<G>(io.mask_in, idx, HL, VL);
-                uint32_t st = 0;
-                int b1 = -1, d = 0;
-                if (moves < 1) { // boardv2.py:44
-                    st = ST_TERMINAL;
-                } else if (io.actions) {
-                    action = io.actions[idx];
-                    if (action < 0 || action >= G::A) {
-                        st = ST_BAD_ACTION;
-                        action = -1;
+                L.reward = 0;
+                L.cascades = 0;
+                L.status = 0;
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+#pragma unroll
+                    for (int j = 0; j < W; j++) L.bd.p[p].w[j] = sl[(O_BD + p * W + j) * NS];
+                idx = (int)sl[O_IDX * NS];
+                L.reward = (int)sl[O_REW * NS];
+                const uint32_t cs = sl[O_CS * NS];
+                L.cascades = (int)(cs & 0xffffu);
+                L.status = cs >> 16;
+            }
+        }
+        if (phase != FIN) {
+            // the Philox block of this cascade iteration (block 0 holds the action pick and the first refill words)
+            uint32_t blk[4];
+            const uint32_t blk_index = phase == FREE ? 0u : (uint32_t)L.cascades * 512u;
+            const unsigned long long board = rf.board0 + (unsigned long long)idx;
+            philox4x32_10(blk_index, rf.step_ctr, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)rf.key,
+                          (uint32_t)(rf.key >> 32), blk);
+            if (phase == FREE) {
+                // ---- BEGIN
+                if (on) {
+                    int b1 = -1, d = 0;
+                    if (moves < 1) { // boardv2.py:44
+                        st = ST_TERMINAL;
+                    } else if (io.actions) {
+                        action = io.actions[idx];
+                        if (action < 0 || action >= G::A) {
+                            st = ST_BAD_ACTION;
+                            action = -1;
+                        }
+                    } else { // board.random_action(): uniform over the legal set of the current board
+                        const int c = swaps_count<G>(HL, VL);
+                        if (c == 0) {
+                            st = ST_NO_LEGAL;
+                        } else {
+                            bool vertical;
+                            b1 = swaps_select_bit<G>(HL, VL, (int)mulhi32(blk[0], (uint32_t)c), vertical);
+                            d = vertical ? G::S : 1;
+                            action = action_of_swap<G>(b1, vertical);
+                        }
                     }
-                } else { // board.random_action(): uniform over the legal set of the current board
-                    const int c = swaps_count<G>(HL, VL);
-                    if (c == 0) {
-                        st = ST_NO_LEGAL;
-                    } else {
-                        uint32_t blk[4];
-                        const unsigned long long board = rf.board0 + (unsigned long long)idx;
-                        philox4x32_10(0u, rf.step_ctr, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)rf.key,
-                                      (uint32_t)(rf.key >> 32), blk);
-                        bool vertical;
-                        b1 = swaps_select_bit<G>(HL, VL, (int)mulhi32(blk[0], (uint32_t)c), vertical);
-                        d = vertical ? G::S : 1;
-                        action = action_of_swap<G>(b1, vertical);
+                    if (action >= 0) {
+                        if (b1 < 0) { // action given by the caller: boardConfig.decode
+                            int b2;
+                            decode_action<G>(action, b1, b2);
+                            d = b2 - b1;
+                        }
+                        handoff = step_begin_at<SH, true>(L, b1, d);
+                        dest = handoff ? FREE : cascade_class<SH>(L);
+                    } else { // a no-op board: FINISH writes it (action -1, nothing stepped)
+                        L.status = st;
+                        dest = FIN;
                     }
                 }
-                if (action >= 0) {
-                    if (b1 < 0) { // action given by the caller: boardConfig.decode
-                        int b2;
-                        decode_action<G>(action, b1, b2);
-                        d = b2 - b1;
+            } else {
+                // ---- ITERATE: one cascade iteration on slots of class `phase`
+                if (on) {
+#pragma unroll
+                    for (int j = 0; j < W; j++) L.cleared.w[j] = sl[(O_CL + j) * NS];
+                    if (phase == OTHER) {
+#pragma unroll
+                        for (int j = 0; j < W; j++) {
+                            L.sp.w[j] = sl[(O_SP + j) * NS];
+                            L.sk0.w[j] = sl[(O_K0 + j) * NS];
+                            L.sk1.w[j] = sl[(O_K1 + j) * NS];
+                        }
+                    } else {
+                        L.sp = bb_zero<W>();
+                        L.sk0 = bb_zero<W>();
+                        L.sk1 = bb_zero<W>();
                     }
-                    handoff = step_begin_at<SH, true>(L, b1, d);
-                    if (!handoff) {
-                        L.status |= st;
-                        dest = cascade_class<SH>(L);
-                    }
-                } else { // no-op boards are finished on the spot
-                    if (io.mask_out) legal_of<SH>(L.bd, HL, VL);
-                    finish_board<SH, true>(rf, io, idx, idx, L.bd, false, -1, moves, 0, 0, st, HL, VL, 0u);
+                    PhiloxRng rng;
+                    rng.init(rf.key, rf.board0 + (unsigned long long)idx, rf.step_ctr);
+                    rng.preset_block(blk_index, blk);
+                    const bool fin = step_iter<SH, PhiloxRng, true, true>(L, rng, (uint32_t)types, HL, VL, handoff);
+                    dest = handoff ? FREE : fin ? FIN : cascade_class<SH>(L);
                 }
             }
-            const unsigned am = __ballot_sync(FULL, dest >= 0);
-            {
-                if (dest >= 0) {
-                    id = lists[FREE * NS + cnt[FREE] - 1 - __popc(am & lt)];
-                    uint32_t *sl = pool + id;
+            // ---- keep the lane in its slot
+            if (dest >= 0 && dest <= FIN) {
 #pragma unroll
-                    for (int p = 0; p < 4; p++)
+                for (int p = 0; p < 4; p++)
 #pragma unroll
-                        for (int j = 0; j < W; j++) sl[(O_BD + p * W + j) * NS] = L.bd.p[p].w[j];
+                    for (int j = 0; j < W; j++) sl[(O_BD + p * W + j) * NS] = L.bd.p[p].w[j];
+                sl[O_REW * NS] = (uint32_t)L.reward;
+                sl[O_CS * NS] = (uint32_t)L.cascades | (L.status << 16);
+                if (phase == FREE) {
+                    sl[O_IDX * NS] = (uint32_t)idx;
+                    sl[O_ACT * NS] = (uint32_t)action;
+                }
+                if (dest < FIN) {
 #pragma unroll
                     for (int j = 0; j < W; j++) sl[(O_CL + j) * NS] = L.cleared.w[j];
                     if (dest == OTHER) {
@@ -939,127 +997,46 @@ __global__ void __launch_bounds__(POOL_BLOCK, 1) pool_step_kernel(RefillDev rf, 
                             sl[(O_K1 + j) * NS] = L.sk1.w[j];
                         }
                     }
-                    sl[O_IDX * NS] = (uint32_t)idx;
-                    sl[O_ACT * NS] = (uint32_t)action;
-                    sl[O_REW * NS] = 0u;
-                    sl[O_CS * NS] = L.status << 16;
                 }
             }
-            cnt[FREE] -= __popc(am);
-            push(dest, id);
-            hand_over(handoff, idx);
-            __syncwarp();
-        } else if (phase == FIN) {
+        } else if (on) {
             // ---- FINISH: legal swaps of the final board, outputs
-            int id = 0, idx = 0;
-            bool handoff = false;
-            if (lane < k) {
-                id = lists[FIN * NS + cnt[FIN] - k + lane];
-                const uint32_t *sl = pool + id;
-                Board<G> bd;
-#pragma unroll
-                for (int p = 0; p < 4; p++)
-#pragma unroll
-                    for (int j = 0; j < W; j++) bd.p[p].w[j] = sl[(O_BD + p * W + j) * NS];
-                idx = (int)sl[O_IDX * NS];
-                const int action = (int)sl[O_ACT * NS];
-                const int reward = (int)sl[O_REW * NS];
-                const uint32_t cs = sl[O_CS * NS];
-                BB<W> HL, VL;
-                legal_of<SH>(bd, HL, VL);
-                if (!any(HL | VL)) { // the shuffle loop: exact kernel
-                    handoff = true;
-                } else {
-                    const int moves = io.moves_left ? io.moves_left[idx] - 1 : 0;
-                    finish_board<SH, true>(rf, io, idx, idx, bd, true, action, moves, reward, (int)(cs & 0xffffu),
-                                           cs >> 16, HL, VL, 0u);
-                }
+            action = (int)sl[O_ACT * NS];
+            legal_of<SH>(L.bd, HL, VL);
+            dest = FREE;
+            if (!any(HL | VL)) { // the shuffle loop (or a no-op board without a legal swap): exact kernel
+                handoff = true;
+            } else {
+                const bool stepped = action >= 0;
+                moves = io.moves_left ? io.moves_left[idx] - (stepped ? 1 : 0) : (stepped ? 0 : 1);
+                finish_board<SH, true>(rf, io, idx, idx, L.bd, stepped, action, moves, L.reward, L.cascades, L.status, HL,
+                                       VL, 0u);
             }
-            cnt[FIN] -= k;
-            push(lane < k ? FREE : -1, id);
-            hand_over(handoff, idx);
-            __syncwarp();
-        } else {
-            // ---- ITERATE: one cascade iteration on k slots of class `phase`
-            int id = 0, idx = 0, dest = -1;
-            bool handoff = false;
-            int have = 0;
-#pragma unroll
-            for (int c = 0; c < CASCADE_CLASSES; c++)
-                if (phase == c) have = cnt[c];
-            if (lane < k) {
-                id = lists[phase * NS + have - k + lane];
-                uint32_t *sl = pool + id;
-                Lane<SH> L;
-#pragma unroll
-                for (int p = 0; p < 4; p++)
-#pragma unroll
-                    for (int j = 0; j < W; j++) L.bd.p[p].w[j] = sl[(O_BD + p * W + j) * NS];
-#pragma unroll
-                for (int j = 0; j < W; j++) L.cleared.w[j] = sl[(O_CL + j) * NS];
-                if (phase == OTHER) {
-#pragma unroll
-                    for (int j = 0; j < W; j++) {
-                        L.sp.w[j] = sl[(O_SP + j) * NS];
-                        L.sk0.w[j] = sl[(O_K0 + j) * NS];
-                        L.sk1.w[j] = sl[(O_K1 + j) * NS];
-                    }
-                } else {
-                    L.sp = bb_zero<W>();
-                    L.sk0 = bb_zero<W>();
-                    L.sk1 = bb_zero<W>();
-                }
-                idx = (int)sl[O_IDX * NS];
-                L.reward = (int)sl[O_REW * NS];
-                const uint32_t cs = sl[O_CS * NS];
-                L.cascades = (int)(cs & 0xffffu);
-                L.status = cs >> 16;
-                // the Philox block of this cascade iteration (block 0 also holds the action pick)
-                PhiloxRng rng;
-                const unsigned long long board = rf.board0 + (unsigned long long)idx;
-                rng.init(rf.key, board, rf.step_ctr);
-                {
-                    uint32_t blk[4];
-                    const uint32_t blk_index = (uint32_t)L.cascades * 512u;
-                    philox4x32_10(blk_index, rf.step_ctr, (uint32_t)board, (uint32_t)(board >> 32), (uint32_t)rf.key,
-                                  (uint32_t)(rf.key >> 32), blk);
-                    rng.preset_block(blk_index, blk);
-                }
-                BB<W> HL, VL;
-                const bool fin = step_iter<SH, PhiloxRng, true, true>(L, rng, (uint32_t)types, HL, VL, handoff);
-                if (handoff) {
-                    dest = FREE;
-                } else {
-                    dest = fin ? FIN : cascade_class<SH>(L);
-#pragma unroll
-                    for (int p = 0; p < 4; p++)
-#pragma unroll
-                        for (int j = 0; j < W; j++) sl[(O_BD + p * W + j) * NS] = L.bd.p[p].w[j];
-                    sl[O_REW * NS] = (uint32_t)L.reward;
-                    sl[O_CS * NS] = (uint32_t)L.cascades | (L.status << 16);
-                    if (!fin) {
-#pragma unroll
-                        for (int j = 0; j < W; j++) sl[(O_CL + j) * NS] = L.cleared.w[j];
-                        if (dest == OTHER) {
-#pragma unroll
-                            for (int j = 0; j < W; j++) {
-                                sl[(O_SP + j) * NS] = L.sp.w[j];
-                                sl[(O_K0 + j) * NS] = L.sk0.w[j];
-                                sl[(O_K1 + j) * NS] = L.sk1.w[j];
-                            }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < CASCADE_CLASSES; c++)
-                if (phase == c) cnt[c] -= k;
-            push(dest, id);
-            hand_over(handoff, idx);
-            __syncwarp();
         }
+        // ---- list the slot, hand boards over
+        {
+            // one shared-memory atomic per thread: the LSU pipe idles in this kernel, the ALU pipe is what it runs on
+            // (warp-aggregated appends cost ~40 ALU instructions per list)
+            if (dest >= 0) {
+                int at = 0;
+#pragma unroll
+                for (int c = 0; c < POOL_LISTS; c++)
+                    if (dest == c) at = c * NS + cnt[c];
+                lists[at + atomicAdd(delta + cur * 8 + dest, 1)] = (uint16_t)id;
+            }
+            const unsigned hm = __ballot_sync(FULL, handoff);
+            if (hm) {
+                int base = 0;
+                if (lane == __ffs((int)hm) - 1) base = atomicAdd(io.handoff, __popc(hm));
+                base = __shfl_sync(FULL, base, __ffs((int)hm) - 1);
+                if (handoff) io.handoff[1 + base + __popc(hm & lt)] = idx;
+            }
+        }
+        cur ^= 1;
     }
 }
+
+#endif // ECG_POOL
 
 // ------------------------------------------------------------------ launchers
 
@@ -1166,29 +1143,34 @@ void launch_jobs(RefillDev rf, StepDev io, int types, long long n, cudaStream_t 
     lane_kernel<SH, PHILOX, false, false><<<sms * ECG_JOBS_PER_SM, ECG_JOBS_BLOCK, 0, s>>>(rf, io, ro, types, (int)n);
 }
 
-// The two-kernel step (Philox mode, or replay mode with tile tables): the common-case kernel over all boards, then the
-// exact kernel over the jobs it handed off (their number is read on the device: no host synchronisation in between)
-// The pooled common-case kernel: one block per SM, no more blocks than there are tiles for their warps
+#if ECG_POOL
+// The pooled common-case kernel: POOL_PER_SM blocks per SM; a block needs a few dozen passes to amortise filling and
+// draining its pool, so small batches stay with the lane kernel
+#ifndef ECG_POOL_MIN_GROUPS
+#define ECG_POOL_MIN_GROUPS 16
+#endif
 template <class SH>
-void launch_pool_step(RefillDev rf, StepDev io, long long n, cudaStream_t s) {
+bool launch_pool_step(RefillDev rf, StepDev io, long long n, cudaStream_t s) {
     using PG = PoolGeo<SH>;
-    constexpr int SMEM = (POOL_BLOCK / 32) * PG::WARP_BYTES;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
+    constexpr int SMEM = PG::BLOCK_BYTES;
+    static int blocks = 0;
+    if (blocks == 0) {
+        int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(pool_step_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        blocks = sms * POOL_PER_SM;
     }
-    const long long tiles = (n + 31) / 32;
-    const long long blocks = (tiles + (POOL_BLOCK / 32) - 1) / (POOL_BLOCK / 32);
-    pool_step_kernel<SH><<<(unsigned)(blocks < sms ? blocks : sms), POOL_BLOCK, SMEM, s>>>(rf, io, io.types, (int)n);
+    long long min_boards = (long long)blocks * POOL_BLOCK * ECG_POOL_MIN_GROUPS;
+    if (const char *e = getenv("ECG_POOL_MIN_BOARDS")) min_boards = atoll(e); // tests: 0 runs every batch through the pool
+    if (n < min_boards) return false;
+    pool_step_kernel<SH><<<blocks, POOL_BLOCK, SMEM, s>>>(rf, io, io.types, (int)n);
+    return true;
 }
+#endif // ECG_POOL
 
-#if !defined(ECG_POOL)
-#define ECG_POOL 0 // measured slower than the lane kernel (profiles/r10_warp_pool_*): off
-#endif
-
+// The two-kernel step (Philox mode, or replay mode with tile tables): the common-case kernel over all boards, then the
+// exact kernel over the jobs it handed off (their number is read on the device: no host synchronisation in between)
 template <class SH, bool PHILOX>
 void launch_two_kernel_step(RefillDev rf, StepDev io, long long n, cudaStream_t s) {
     const RolloutDev ro = {};
@@ -1196,10 +1178,7 @@ void launch_two_kernel_step(RefillDev rf, StepDev io, long long n, cudaStream_t 
     bool pooled = false;
 #if ECG_POOL
     if constexpr (PHILOX && PoolGeo<SH>::OK) {
-        if (!io.src_index) {
-            launch_pool_step<SH>(rf, io, n, s);
-            pooled = true;
-        }
+        if (!io.src_index) pooled = launch_pool_step<SH>(rf, io, n, s);
     }
 #endif
     if (!pooled) launch_lanes<SH, PHILOX, false, true>(rf, io, ro, io.types, n, s);
