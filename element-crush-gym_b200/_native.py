@@ -74,6 +74,12 @@ EXPORTS = {
     "ecg_episode_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecg_augment": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int64, C.c_void_p]),
     "ecg_observe_onehot": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    "ecg_host_expand_nibbles": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64]),
+    "ecg_host_expander_create": (C.c_void_p, [C.c_int]),
+    "ecg_host_expander_submit": (C.c_int, [C.c_void_p, C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                           C.c_int]),
+    "ecg_host_expander_wait": (C.c_int, [C.c_void_p]),
+    "ecg_host_expander_destroy": (None, [C.c_void_p]),
 }
 
 _lib = None

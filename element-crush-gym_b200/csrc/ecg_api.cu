@@ -2,9 +2,17 @@
 // kernel objects (ecg_shape_kernels.cu), and the two size-independent kernels.
 #include <cuda_runtime.h>
 
+#include <immintrin.h>
+
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../include/ecg.h"
 #include "ecg_core.cuh"
@@ -435,3 +443,211 @@ int ecg_episode_stats(const int32_t *score, const uint8_t *flags, int64_t *out, 
     return check_launch("ecg_episode_stats");
 }
 }
+
+// ------------------------------------------------------------------ host side of the compact observation
+
+namespace {
+
+struct ExpandGeo {
+    int rc, nb;        // cells and nibble bytes per board
+    uint8_t lut[16];   // code -> cell value (boardConfig.py:29-43)
+    uint16_t tab[256]; // nibble byte -> two cell values (low nibble first)
+};
+
+ExpandGeo expand_geo(const ecg_config *cfg) {
+    ExpandGeo g;
+    g.rc = cfg->rows * cfg->cols;
+    g.nb = (g.rc + 1) / 2;
+    for (int c = 0; c < 12; c++) g.lut[c] = (uint8_t)c;
+    g.lut[12] = (uint8_t)cfg->h_line;
+    g.lut[13] = (uint8_t)cfg->v_line;
+    g.lut[14] = (uint8_t)cfg->bomb;
+    g.lut[15] = (uint8_t)cfg->mega_token;
+    for (int b = 0; b < 256; b++) g.tab[b] = (uint16_t)(g.lut[b & 15] | (g.lut[b >> 4] << 8));
+    return g;
+}
+
+void expand_scalar(const ExpandGeo &g, const uint8_t *src, uint8_t *dst, int from_byte) {
+    for (int k = from_byte; k < g.nb; k++) {
+        const uint16_t v = g.tab[src[k]];
+        dst[2 * k] = (uint8_t)v;
+        if (2 * k + 1 < g.rc) dst[2 * k + 1] = (uint8_t)(v >> 8);
+    }
+}
+
+// 16 nibble bytes -> 32 cell bytes: two table lookups (pshufb) and an interleave
+__attribute__((target("ssse3"))) inline void expand16(const __m128i lut, const uint8_t *src, uint8_t *dst) {
+    const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src));
+    const __m128i m = _mm_set1_epi8(0x0F);
+    const __m128i lo = _mm_shuffle_epi8(lut, _mm_and_si128(x, m));
+    const __m128i hi = _mm_shuffle_epi8(lut, _mm_and_si128(_mm_srli_epi16(x, 4), m));
+    _mm_storeu_si128(reinterpret_cast<__m128i *>(dst), _mm_unpacklo_epi8(lo, hi));
+    _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + 16), _mm_unpackhi_epi8(lo, hi));
+}
+
+// Boards of 16+ nibble bytes: whole 16-byte blocks, then one block that ends with the board's last byte (it overlaps
+// the previous one).  With an odd cell count that block writes one byte past the board -- the first byte of the next
+// board, which is written afterwards -- so the last board of a range takes the scalar tail instead.
+__attribute__((target("ssse3"))) void expand_range_ssse3(const ExpandGeo &g, const uint8_t *nib, uint8_t *cells,
+                                                         int64_t n) {
+    const __m128i lut = _mm_loadu_si128(reinterpret_cast<const __m128i *>(g.lut));
+    const int full = g.nb / 16 * 16, tail = g.nb - 16;
+    const bool spill = (g.rc & 1) != 0;
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t *src = nib + i * g.nb;
+        uint8_t *dst = cells + i * g.rc;
+        for (int off = 0; off < full; off += 16) expand16(lut, src + off, dst + 2 * off);
+        if (full < g.nb) {
+            if (spill && i == n - 1) expand_scalar(g, src, dst, full);
+            else expand16(lut, src + tail, dst + 2 * tail);
+        }
+    }
+}
+
+// The same through a stack buffer of 16 boards (16 * rc bytes: a whole number of 16-byte blocks) that leaves with
+// non-temporal stores: the output is written once and not read again by these threads, and a cached store would first
+// read every line it is about to overwrite (1.36 GB of extra DRAM reads per 2^24 9x9 boards).  cells must be 16-byte
+// aligned; n a multiple of 16.
+__attribute__((target("ssse3"))) void expand_range_ssse3_nt(const ExpandGeo &g, const uint8_t *nib, uint8_t *cells,
+                                                            int64_t n) {
+    const __m128i lut = _mm_loadu_si128(reinterpret_cast<const __m128i *>(g.lut));
+    const int full = g.nb / 16 * 16, tail = g.nb - 16;
+    alignas(64) uint8_t buf[16 * 256 + 32];
+    for (int64_t i0 = 0; i0 < n; i0 += 16) {
+        for (int k = 0; k < 16; k++) {
+            const uint8_t *src = nib + (i0 + k) * g.nb;
+            uint8_t *dst = buf + k * g.rc;
+            for (int off = 0; off < full; off += 16) expand16(lut, src + off, dst + 2 * off);
+            if (full < g.nb) expand16(lut, src + tail, dst + 2 * tail);
+        }
+        __m128i *out = reinterpret_cast<__m128i *>(cells + i0 * g.rc);
+        const __m128i *in = reinterpret_cast<const __m128i *>(buf);
+        for (int q = 0; q < g.rc; q++) _mm_stream_si128(out + q, _mm_load_si128(in + q));
+    }
+    _mm_sfence();
+}
+
+void expand_range(const ExpandGeo &g, const uint8_t *nib, uint8_t *cells, int64_t n) {
+    static const bool ssse3 = __builtin_cpu_supports("ssse3");
+    static const bool nt = !(getenv("ECG_EXPAND_NT") && getenv("ECG_EXPAND_NT")[0] == '0');
+    if (ssse3 && g.nb >= 16) {
+        const int64_t n16 = (nt && (reinterpret_cast<uintptr_t>(cells) & 15u) == 0) ? (n & ~(int64_t)15) : 0;
+        if (n16) expand_range_ssse3_nt(g, nib, cells, n16);
+        if (n16 < n) expand_range_ssse3(g, nib + n16 * g.nb, cells + n16 * g.rc, n - n16);
+        return;
+    }
+    for (int64_t i = 0; i < n; i++) expand_scalar(g, nib + i * g.nb, cells + i * g.rc, 0);
+}
+
+struct Expander {
+    struct Job {
+        ExpandGeo g;
+        const uint8_t *nib;
+        uint8_t *cells;
+        int64_t n;
+        cudaEvent_t event;
+    };
+    std::vector<std::thread> workers;
+    std::deque<Job> queue;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    int64_t pending = 0;
+    int device = 0;
+    bool stop = false, failed = false;
+    char err[200] = "";
+
+    explicit Expander(int threads) {
+        cudaGetDevice(&device);
+        for (int t = 0; t < threads; t++) workers.emplace_back([this] { run(); });
+    }
+    ~Expander() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &w : workers) w.join();
+    }
+    void run() {
+        cudaSetDevice(device); // the events belong to the creator's device
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [this] { return stop || !queue.empty(); });
+                if (queue.empty()) return;
+                j = queue.front();
+                queue.pop_front();
+            }
+            cudaError_t e = j.event ? cudaEventSynchronize(j.event) : cudaSuccess;
+            if (e == cudaSuccess) expand_range(j.g, j.nib, j.cells, j.n);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (e != cudaSuccess && !failed) {
+                    failed = true;
+                    snprintf(err, sizeof(err), "ecg_host_expander: %s", cudaGetErrorString(e));
+                }
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+int ecg_host_expand_nibbles(const ecg_config *cfg, const uint8_t *nibbles, uint8_t *cells, int64_t n) {
+    if (check_cfg(cfg)) return -1;
+    if (!nibbles || !cells) return fail("ecg_host_expand_nibbles: NULL buffer");
+    if (n <= 0) return 0;
+    expand_range(expand_geo(cfg), nibbles, cells, n);
+    return 0;
+}
+
+void *ecg_host_expander_create(int threads) {
+    if (threads < 1 || threads > 1024) {
+        fail("ecg_host_expander_create: threads must be in 1..1024");
+        return nullptr;
+    }
+    return new Expander(threads);
+}
+
+int ecg_host_expander_submit(void *expander, const ecg_config *cfg, const uint8_t *nibbles, uint8_t *cells, int64_t n,
+                             void *event, int split) {
+    if (!expander) return fail("ecg_host_expander_submit: NULL expander");
+    if (check_cfg(cfg)) return -1;
+    if (!nibbles || !cells) return fail("ecg_host_expander_submit: NULL buffer");
+    if (n <= 0) return 0;
+    Expander *x = static_cast<Expander *>(expander);
+    if (split < 1) split = 1;
+    if (split > n) split = (int)n;
+    const ExpandGeo g = expand_geo(cfg);
+    {
+        std::lock_guard<std::mutex> lk(x->mu);
+        for (int s = 0; s < split; s++) { // pieces start at multiples of 16 boards (16-byte aligned output)
+            const int64_t lo = (n * s / split) & ~(int64_t)15, hi = s + 1 == split ? n : (n * (s + 1) / split) & ~(int64_t)15;
+            if (hi <= lo) continue;
+            x->queue.push_back({g, nibbles + lo * g.nb, cells + lo * g.rc, hi - lo, (cudaEvent_t)event});
+            x->pending++;
+        }
+    }
+    x->cv_work.notify_all();
+    return 0;
+}
+
+int ecg_host_expander_wait(void *expander) {
+    if (!expander) return fail("ecg_host_expander_wait: NULL expander");
+    Expander *x = static_cast<Expander *>(expander);
+    std::unique_lock<std::mutex> lk(x->mu);
+    x->cv_done.wait(lk, [x] { return x->pending == 0; });
+    if (x->failed) {
+        x->failed = false;
+        return fail(x->err);
+    }
+    return 0;
+}
+
+void ecg_host_expander_destroy(void *expander) { delete static_cast<Expander *>(expander); }
+
+} // extern "C"

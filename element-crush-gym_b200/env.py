@@ -100,13 +100,22 @@ class HostStepper:
     obs_format="nibbles": the same information in about half the PCIe bytes (PCIe is the whole e2e cost: the step
         kernel is 20x faster than the copies): observation uint8 [N, ceil(H*W/2)] of 4-bit cell CODES
         (ecg_unpack_nibbles; `decode_obs` turns it into the uint8 form on the host when wanted), reward int16
-        (saturating), actions int16."""
+        (saturating), actions int16.
+    host_expand=True (with obs_format="uint8"): the same outputs as the default, byte for byte, but the observation
+        crosses PCIe as 4-bit codes and a pool of host threads in libecg.so (ecg_host_expander_*) widens every chunk
+        to uint8 cell values as soon as its copy has landed, while later chunks are still in flight:
+        H*W/2 + 6 B out per board and step instead of H*W + 6."""
 
-    def __init__(self, env: BatchedMatch3Env, chunks: int = 16, obs_format: str = "uint8"):
+    def __init__(self, env: BatchedMatch3Env, chunks: int = 16, obs_format: str = "uint8", host_expand: bool = False,
+                 expand_threads: int = None):
         if obs_format not in ("uint8", "nibbles"):
             raise ValueError("obs_format must be 'uint8' or 'nibbles'")
+        if host_expand and obs_format != "uint8":
+            raise ValueError("host_expand widens the 4-bit observation to the uint8 form: obs_format must be 'uint8'")
         self.env = env
         self.obs_format = obs_format
+        self.host_expand = bool(host_expand)
+        self._expander = None
         n = env.num_envs
         self.n = n
         dev = env.board.device
@@ -130,7 +139,7 @@ class HostStepper:
         self.d_actions_in = torch.zeros(n, dtype=small, device=dev) if nib else self.d_actions
         self.d_reward = torch.zeros(n, dtype=small, device=dev) if nib else None
         self.d_tmp32 = torch.zeros(n, dtype=torch.int32, device=dev) if nib else None
-        self.d_obs = torch.zeros(obs_shape, dtype=torch.uint8, device=dev)
+        self.d_obs = None if self.host_expand else torch.zeros(obs_shape, dtype=torch.uint8, device=dev)
         # done / won as 0/1 bytes, split from the flags byte on the device: a host-side pass over N flags per step would
         # cost more than the copy (and torchrun pins the host side to one thread)
         self.d_done = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -141,6 +150,35 @@ class HostStepper:
         self.h2d_bytes = n * a_bytes
         self.d2h_bytes = n * (self.h_obs[0].numel() + a_bytes + 2)
         self.action_d2h_bytes = n * a_bytes  # random_action(): the pick the host sends back in
+        if self.host_expand:
+            import ctypes as C
+            import os
+            nb = (R * Cc + 1) // 2
+            self.d_nib = torch.zeros((n, nb), dtype=torch.uint8, device=dev)
+            self.h_nib = torch.zeros((n, nb), dtype=torch.uint8, **pin)
+            self.events = [torch.cuda.Event() for _ in self.bounds]
+            if expand_threads is None:
+                local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+                # two cores stay free for the thread that queues the chunks and the driver's own threads; past ~12
+                # threads the widening is bound by host memory bandwidth anyway (r10: 8 / 12 / 14 / 16 threads ->
+                # 24.8 / 22.2 / 21.2 / 22.3 ms per 2^24-board step on a 16-core host)
+                expand_threads = max(1, ((os.cpu_count() or 1) - 2) // max(local, 1))
+            self.expand_threads = int(expand_threads)
+            self._expander = C.c_void_p(env.board.L.ecg_host_expander_create(self.expand_threads))
+            if not self._expander:
+                raise N.EcgError("ecg_host_expander_create failed: " + env.board.L.ecg_last_error().decode())
+            self.d2h_bytes = n * (nb + a_bytes + 2)
+
+    def close(self):
+        if self._expander:
+            self.env.board.L.ecg_host_expander_destroy(self._expander)
+            self._expander = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _chunk_call(self, lo, hi, fn_step):
         b = self.env.board
@@ -184,7 +222,7 @@ class HostStepper:
         nib = self.obs_format == "nibbles"
         src = self.h_actions if actions_host is None else actions_host
         cur = torch.cuda.current_stream(self.dev)
-        for (lo, hi), st in zip(self.bounds, self.streams):
+        for k, ((lo, hi), st) in enumerate(zip(self.bounds, self.streams)):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 self.d_actions_in[lo:hi].copy_(src[lo:hi], non_blocking=True)
@@ -200,11 +238,23 @@ class HostStepper:
                     torch.clamp(b.step_reward[lo:hi], max=32767, out=self.d_tmp32[lo:hi])  # saturate, then narrow
                     self.d_reward[lo:hi].copy_(self.d_tmp32[lo:hi])
                     self.h_reward[lo:hi].copy_(self.d_reward[lo:hi], non_blocking=True)
+                elif self.host_expand:
+                    N.check(L.ecg_unpack_nibbles(C.byref(b.nat), boards, C.c_void_p(self.d_nib[lo:].data_ptr()),
+                                                 hi - lo, sp), "ecg_unpack_nibbles")
+                    self.h_nib[lo:hi].copy_(self.d_nib[lo:hi], non_blocking=True)
+                    ev = self.events[k]
+                    ev.record(st)
+                    N.check(L.ecg_host_expander_submit(self._expander, C.byref(b.nat),
+                                                       C.c_void_p(self.h_nib[lo:].data_ptr()),
+                                                       C.c_void_p(self.h_obs[lo:].data_ptr()), hi - lo,
+                                                       C.c_void_p(ev.cuda_event), 4), "ecg_host_expander_submit")
+                    self.h_reward[lo:hi].copy_(b.step_reward[lo:hi], non_blocking=True)
                 else:
                     N.check(L.ecg_unpack(C.byref(b.nat), boards, C.c_void_p(self.d_obs[lo:].data_ptr()), 1, hi - lo,
                                          sp), "ecg_unpack")
                     self.h_reward[lo:hi].copy_(b.step_reward[lo:hi], non_blocking=True)
-                self.h_obs[lo:hi].copy_(self.d_obs[lo:hi], non_blocking=True)
+                if not self.host_expand:
+                    self.h_obs[lo:hi].copy_(self.d_obs[lo:hi], non_blocking=True)
                 torch.bitwise_and(b.flags[lo:hi], N.FLAG_DONE, out=self.d_done[lo:hi])
                 torch.bitwise_right_shift(b.flags[lo:hi], 1, out=self.d_won[lo:hi])  # FLAG_WON == 2, the top flag
                 self.h_done[lo:hi].copy_(self.d_done[lo:hi].view(torch.bool), non_blocking=True)
@@ -212,6 +262,8 @@ class HostStepper:
         for st in self.streams:
             cur.wait_stream(st)
         cur.synchronize()
+        if self.host_expand:
+            N.check(L.ecg_host_expander_wait(self._expander), "ecg_host_expander_wait")
         b._mask_valid = True
         b.step_ctr += 1
         b._moves_bound = max(b._moves_bound - 1, 0)

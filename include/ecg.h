@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ECG_VERSION 105
+#define ECG_VERSION 106
 
 /* per-board status bits */
 #define ECG_ST_TERMINAL 1        /* n_actions < 1: board returned unchanged (boardv2.py:44-45) */
@@ -198,6 +198,22 @@ int ecg_observe_onehot(const ecg_config *cfg, const void *boards, void *out, int
  * dataset.py:99-107) is a fixed permutation of the action ids and lives in the host layer. */
 int ecg_augment(const ecg_config *cfg, const void *boards_in, void *boards_out, int mirror, const uint8_t *type_perm,
                 int64_t n, void *stream);
+
+/* Host side of the compact observation (no CUDA kernel): 4-bit cell codes in HOST memory (the ecg_unpack_nibbles
+ * layout, e.g. the pinned buffer a D2H copy filled) -> BoardV2.array as uint8 cell VALUES [n, rows, cols] (env.py:56),
+ * byte-identical to ecg_unpack(..., elem_bytes = 1) of the same boards.  PCIe is the whole end-to-end cost of a step
+ * (the observation is 81 of 91 bytes per 9x9 board): crossing it with 41 bytes and widening on the host cores halves
+ * the transfer.  Single-threaded; the expander below runs it on a pool of host threads. */
+int ecg_host_expand_nibbles(const ecg_config *cfg, const uint8_t *nibbles, uint8_t *cells, int64_t n);
+/* A pool of `threads` host threads (bound to the calling thread's CUDA device).  submit() queues the expansion of n
+ * boards, cut into `split` >= 1 pieces; a piece starts once `event` (a cudaEvent_t recorded after the D2H copy of the
+ * nibbles, or NULL) has completed, so chunks are widened while later chunks are still crossing PCIe.  wait() blocks
+ * until everything submitted is done and returns 0, or -1 with ecg_last_error() if a piece failed. */
+void *ecg_host_expander_create(int threads);
+int ecg_host_expander_submit(void *expander, const ecg_config *cfg, const uint8_t *nibbles, uint8_t *cells, int64_t n,
+                             void *event, int split);
+int ecg_host_expander_wait(void *expander);
+void ecg_host_expander_destroy(void *expander);
 
 /* episode statistics (main.py:240-267 sample()): out[0]=sum(score) out[1]=n out[2]=min out[3]=max
  * out[4]=#flags&WON out[5]=sum(score^2); out must be zero-initialised except out[2]=INT64_MAX, out[3]=INT64_MIN */

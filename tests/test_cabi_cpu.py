@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(E):
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(E._native.EXPORTS), declared ^ set(E._native.EXPORTS)
-    assert E._native.lib().ecg_version() == 105
+    assert E._native.lib().ecg_version() == 106
 
 
 def test_struct_layouts_match_header(E):
@@ -133,3 +133,41 @@ def test_product_package_never_uses_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src.replace("tests/hostsim", "")), f
+
+
+@pytest.mark.parametrize("size", [4, 5, 6, 8, 9, 11, 16])
+def test_host_expand_nibbles_matches_the_code_table(E, size):
+    """ecg_host_expand_nibbles / the expander pool (host code, no CUDA): 4-bit codes -> uint8 cell values, every code,
+    odd and even cell counts, boards below and above the 16-byte SIMD block, ranges cut at every board"""
+    import numpy as np
+    N = E._native
+    L = N.lib()
+    types = 11 if size % 2 else 6
+    cfg = N.make_config(size, size, types)
+    rc, nb = size * size, (size * size + 1) // 2
+    lut = np.array(list(range(12)) + [cfg.h_line, cfg.v_line, cfg.bomb, cfg.mega_token], dtype=np.uint8)
+    rng = np.random.default_rng(size)
+    n = 1003
+    nib = rng.integers(0, 256, size=(n, nb), dtype=np.uint8)
+    want = np.empty((n, nb * 2), dtype=np.uint8)
+    want[:, 0::2] = lut[nib & 15]
+    want[:, 1::2] = lut[nib >> 4]
+    want = np.ascontiguousarray(want[:, :rc])
+    guard = 64
+    out = np.full(n * rc + guard, 0xEE, dtype=np.uint8)
+    assert L.ecg_host_expand_nibbles(C.byref(cfg), nib.ctypes.data, out.ctypes.data, n) == 0
+    assert np.array_equal(out[:n * rc].reshape(n, rc), want) and (out[n * rc:] == 0xEE).all()
+    x = L.ecg_host_expander_create(5)
+    assert x
+    try:
+        out[:] = 0xEE
+        for lo, hi, split in ((0, 1, 1), (1, 2, 7), (2, 500, 13), (500, n, 64)):
+            assert L.ecg_host_expander_submit(x, C.byref(cfg), nib[lo:].ctypes.data, out[lo * rc:].ctypes.data, hi - lo,
+                                              None, split) == 0
+        assert L.ecg_host_expander_wait(x) == 0
+        assert np.array_equal(out[:n * rc].reshape(n, rc), want) and (out[n * rc:] == 0xEE).all()
+        assert L.ecg_host_expander_wait(x) == 0  # nothing pending: returns at once
+    finally:
+        L.ecg_host_expander_destroy(x)
+    assert L.ecg_host_expand_nibbles(C.byref(cfg), None, out.ctypes.data, 1) == -1
+    assert b"NULL" in L.ecg_last_error()

@@ -290,22 +290,25 @@ def test_match3env_dropin_contract(E):
     assert np.array_equal(obs2, d["init"][e])  # env.py:62: reset() without a seed keeps the seed
 
 
-@pytest.mark.parametrize("obs_format", ["uint8", "nibbles"])
+@pytest.mark.parametrize("obs_format", ["uint8", "nibbles", "uint8+host_expand"])
 def test_host_stepper_matches_device_api(E, obs_format):
     """HostStepper (host buffers in pinned memory, chunked over CUDA streams: the call bench.py's e2e times) returns
     the same observations, rewards and done / won flags as BatchedMatch3Env.step on a twin environment, and both
     match the oracle (Philox mode, ragged chunk sizes).  obs_format="nibbles" carries the same information in half
-    the PCIe bytes (4-bit cell codes, int16 reward and actions)."""
+    the PCIe bytes (4-bit cell codes, int16 reward and actions); host_expand=True returns the uint8 form, byte for
+    byte, from 4-bit codes widened by the library's host thread pool."""
     import torch
-    n, moves = 3000 + (1 if obs_format == "nibbles" else 0), 6  # not a multiple of the chunk count or of the tile
+    expand = obs_format.endswith("+host_expand")
+    obs_format = obs_format.split("+")[0]
+    n, moves = 3000 + (1 if obs_format == "nibbles" or expand else 0), 6  # not a multiple of the chunk count or of the tile
     o = Oracle(9, 9, 6)
     a_env = E.BatchedMatch3Env(n, seed=11, num_moves=moves, env_goal=60)
     b_env = E.BatchedMatch3Env(n, seed=11, num_moves=moves, env_goal=60)
     boards = np_(a_env.init()).astype(np.int64)
     assert np.array_equal(boards, np_(b_env.init()))
-    hs = E.HostStepper(a_env, chunks=5, obs_format=obs_format)
+    hs = E.HostStepper(a_env, chunks=5, obs_format=obs_format, host_expand=expand, expand_threads=3 if expand else None)
     small = torch.int16 if obs_format == "nibbles" else torch.int32
-    assert hs.d2h_bytes == n * ((41 + 2 + 2) if obs_format == "nibbles" else (81 + 4 + 2))
+    assert hs.d2h_bytes == n * ((41 + 2 + 2) if obs_format == "nibbles" else (41 + 4 + 2) if expand else (81 + 4 + 2))
     score = np.zeros(n, dtype=np.int64)
     for t in range(moves):
         acts = hs.random_action()
