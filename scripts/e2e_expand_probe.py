@@ -14,7 +14,7 @@ def timeit(f, reps=4):
     torch.cuda.synchronize()
     return (time.perf_counter() - t) / reps * 1e3
 for chunks in (16, 32, 64):
-    for threads in (8, 12, 14, 16):
+    for threads in (12, 14):
         hs = E.HostStepper(env, chunks=chunks, host_expand=True, expand_threads=threads)
         a = hs.random_action()
         print(f"chunks={chunks:3d} threads={threads:2d}: random_action {timeit(hs.random_action):6.2f} ms   step {timeit(lambda: hs.step(a)):6.2f} ms", flush=True)
