@@ -56,6 +56,7 @@ struct StepArgs {
     int64_t n;
     int64_t *handoffs; // modes 3 / 4: incremented per board the common-case build handed off
     uint32_t *words;   // optional, replay: raw words consumed by the step
+    int64_t *class_errors; // mode 6: lanes whose pending match contradicts their cascade_class
 };
 
 template <class SH>
@@ -74,6 +75,42 @@ static void step_t(const StepArgs &a) {
             so.status = terminal ? ST_TERMINAL : ST_BAD_ACTION;
             Derived<G> d = derive<SH>(b);
             legal_swaps<SH>(d, eq_at<SH, 1>(d), eq_at<SH, G::S>(d), HL, VL);
+        } else if (a.mode == 6) {
+            // the pooled step kernel's decomposition of the common-case pass: BEGIN, then one step_iter<DEFER_LEGAL>
+            // per pass on a lane whose gravity / refill work its cascade_class predicted, FINISH = the legal swaps of
+            // the final board (a board without any goes to the exact build, like any rare case)
+            PhiloxRng rng;
+            rng.init(a.key, a.board0 + (uint64_t)i, a.step_ctr);
+            Lane<SH> L;
+            L.bd = b;
+            int b1, b2;
+            decode_action<G>(a.actions[i], b1, b2);
+            bool rare = step_begin_at<SH, true>(L, b1, b2 - b1);
+            bool fin = false;
+            while (!rare && !fin) {
+                const int cls = cascade_class<SH>(L);
+                const BB<G::W> spec = L.bd.p[3] & L.bd.p[2];
+                const BB<G::W> gone = L.cleared | spec; // cleared cells (a class 0 / 1 board holds no special)
+                if (cls < 2 && (popcount(gone) != 3 || any(spec) || any(L.sp))) ++*a.class_errors;
+                if (cls == 0 && any(gone & shl<G::S>(gone))) ++*a.class_errors; // three holes in ONE row
+                if (cls == 1 && !any(gone & shl<2 * G::S>(gone))) ++*a.class_errors; // three in one column
+                PhiloxRng r2 = rng;
+                fin = step_iter<SH, PhiloxRng, true, true>(L, r2, (uint32_t)a.types, HL, VL, rare);
+            }
+            if (!rare) {
+                Derived<G> d = derive<SH>(L.bd);
+                legal_swaps<SH>(d, eq_at<SH, 1>(d), eq_at<SH, G::S>(d), HL, VL);
+                rare = !any(HL | VL);
+            }
+            if (rare) {
+                if (a.handoffs) ++*a.handoffs;
+                step_board<SH>(b, a.actions[i], (uint32_t)a.types, rng, so, HL, VL);
+            } else {
+                b = L.bd;
+                so.reward = L.reward;
+                so.cascades = L.cascades;
+                so.status = L.status;
+            }
         } else if (a.mode == 2 || a.mode == 4) { // mode + 2: common-case build first, exact build on a hand-off
             PhiloxRng rng;
             rng.init(a.key, a.board0 + (uint64_t)i, a.step_ctr);
@@ -188,7 +225,7 @@ static void init_t(int types, const uint32_t *raw, int64_t raw_stride, int64_t r
         return 0;                                                \
     } while (0)
 
-static int64_t g_handoffs = 0;
+static int64_t g_handoffs = 0, g_class_errors = 0;
 static uint32_t *g_words = nullptr; // hs_set_words: where the next replay hs_step reports the words each step drew
 
 extern "C" {
@@ -199,8 +236,9 @@ int hs_step(int rows, int cols, int types, int mode, const uint32_t *raw, int64_
             uint8_t *legal, int64_t n) {
     if (rows != cols || types < 1 || types > 11) return -1;
     g_handoffs = 0;
+    g_class_errors = 0;
     StepArgs a = {types, mode, raw, raw_stride, raw_len, key, board0, step_ctr, in, actions, moves_left,
-                  out, reward, cascades, status, legal, n, &g_handoffs, g_words};
+                  out, reward, cascades, status, legal, n, &g_handoffs, g_words, &g_class_errors};
     g_words = nullptr;
     DISPATCH(rows, types, step_t<SH>(a));
 }
@@ -209,6 +247,7 @@ void hs_set_words(uint32_t *words) { g_words = words; }
 
 // boards the common-case build handed off in the last hs_step call (modes 3 / 4)
 int64_t hs_handoffs(void) { return g_handoffs; }
+int64_t hs_class_errors(void) { return g_class_errors; }
 
 int hs_legal(int rows, int cols, int types, const int64_t *boards, uint8_t *legal, int64_t n) {
     if (rows != cols || types < 1 || types > 11) return -1;

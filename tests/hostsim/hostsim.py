@@ -45,6 +45,7 @@ def lib(size):
         build((size,))
         L = C.CDLL(_lib_path(size))
         L.hs_handoffs.restype = C.c_int64
+        L.hs_class_errors.restype = C.c_int64
         _libs[size] = L
     return _libs[size]
 
@@ -59,12 +60,18 @@ class HostSim:
         self.A = rows * (cols - 1) * 2
         self.L = lib(rows)
 
-    def step(self, boards, actions, *, mode, raw=None, key=0, board0=0, step_ctr=0, moves_left=None, two_pass=False):
-        """two_pass: the two-kernel step on the host -- common-case build first, exact build on a hand-off"""
+    def step(self, boards, actions, *, mode, raw=None, key=0, board0=0, step_ctr=0, moves_left=None, two_pass=False,
+             pooled=False):
+        """two_pass: the two-kernel step on the host -- common-case build first, exact build on a hand-off;
+        pooled (Philox): the common-case pass cut the way the pooled step kernel cuts it (BEGIN, step_iter<DEFER_LEGAL>
+        per pass with cascade_class checked against the pending match, legal swaps at FINISH)"""
         boards = np.ascontiguousarray(boards, dtype=np.int64)
         n = boards.shape[0]
         actions = np.ascontiguousarray(actions, dtype=np.int32)
         m = {"replay": 1, "philox": 2}[mode] + (2 if two_pass else 0)
+        if pooled:
+            assert mode == "philox"
+            m = 6
         stride = rawlen = 0
         if raw is not None:
             raw = np.ascontiguousarray(raw, dtype=np.uint32)
@@ -83,7 +90,7 @@ class HostSim:
                             _p(out), _p(reward), _p(casc), _p(status), _p(legal), C.c_int64(n))
         assert rc == 0
         return {"boards": out, "reward": reward, "cascades": casc, "status": status, "legal": legal.astype(bool),
-                "handoffs": int(self.L.hs_handoffs()), "words": words}
+                "handoffs": int(self.L.hs_handoffs()), "words": words, "class_errors": int(self.L.hs_class_errors())}
 
     def legal(self, boards):
         boards = np.ascontiguousarray(boards, dtype=np.int64)

@@ -140,6 +140,35 @@ def test_fuzz_dense_boards_philox(shape):
     assert 0 < r2["handoffs"] < n  # both builds were exercised
 
 
+@pytest.mark.parametrize("shape", [(9, 9, 6), (9, 9, 8), (6, 6, 4), (12, 12, 7)])
+def test_pooled_decomposition_philox(shape):
+    """The pooled step kernel's cut of the common-case pass (csrc/ecg_shape_kernels.cu, -DECG_POOL=1): BEGIN, one
+    step_iter<DEFER_LEGAL> per pass, the legal swaps at FINISH -- same results as the oracle on natural play and on
+    dense boards with planted specials, and cascade_class agrees with the pending match of every pass."""
+    o, h = Oracle(*shape), HostSim(*shape)
+    n = 1200
+    b, _ = h.init(mode="philox", n=n, key=KEY)
+    rng = np.random.default_rng(11)
+    handoffs = 0
+    for step in range(10):
+        lo = o.legal_mask_batch(b)
+        acts = np.array([rng.choice(np.flatnonzero(m)) if m.any() else 0 for m in lo], dtype=np.int32)
+        if step == 5:  # plant specials and an empty cell: the class "everything else", special pairs, extra holes
+            sp = [o.cfg.h_line, o.cfg.v_line, o.cfg.bomb, o.cfg.mega_token]
+            for i in range(0, n, 3):
+                b[i, rng.integers(shape[0]), rng.integers(shape[1])] = sp[rng.integers(4)]
+            for i in range(1, n, 7):
+                b[i, rng.integers(shape[0]), rng.integers(shape[1])] = 0
+        ro = o.step_batch(b, acts, mode="philox", key=KEY, board0=0, step_ctr=step)
+        rp = h.step(b, acts, mode="philox", key=KEY, board0=0, step_ctr=step, pooled=True)
+        for k in ("boards", "reward", "cascades", "status", "legal"):
+            assert np.array_equal(ro[k], rp[k]), (k, step)
+        assert rp["class_errors"] == 0
+        handoffs += rp["handoffs"]
+        b = ro["boards"]
+    assert 0 < handoffs < 0.3 * n * 10
+
+
 @pytest.mark.parametrize("shape", [(9, 9, 6), (6, 6, 4), (12, 12, 7)])
 def test_two_pass_episodes_philox(shape):
     """Natural play (random legal actions from fresh boards, 12 steps): most single crossings are plain triples,
