@@ -334,6 +334,30 @@ def test_host_stepper_matches_device_api(E, obs_format):
         boards = res["boards"]
 
 
+@pytest.mark.parametrize("shape", [(4, 4, 4), (5, 5, 4), (6, 6, 4), (11, 11, 7), (16, 16, 8)])
+def test_host_expand_other_board_sizes(E, shape):
+    """host_expand on boards below the 16-byte SIMD block (scalar table), with odd and even cell counts, and on the
+    largest board: the widened observation equals the device's own uint8 unpack, rewards and flags equal the twin's"""
+    import torch
+    n, moves = 2000 + 37, 3
+    a_env = E.BatchedMatch3Env(n, shape[1], shape[0], shape[2], seed=5, num_moves=moves, env_goal=40)
+    b_env = E.BatchedMatch3Env(n, shape[1], shape[0], shape[2], seed=5, num_moves=moves, env_goal=40)
+    a_env.init()
+    b_env.init()
+    hs = E.HostStepper(a_env, chunks=3, host_expand=True, expand_threads=4, expand_pieces=3)
+    try:
+        for t in range(moves):
+            acts = hs.random_action()
+            obs, rew, done, won, _ = hs.step(acts)
+            obs2, rew2, done2, won2, _ = b_env.step(acts.to(b_env.board.device))
+            assert obs.shape == (n, shape[0], shape[1]) and obs.dtype == torch.uint8
+            assert np.array_equal(obs.numpy(), np_(obs2)) and np.array_equal(rew.numpy(), np_(rew2))
+            assert np.array_equal(done.numpy(), np_(done2)) and np.array_equal(won.numpy(), np_(won2))
+            assert np.array_equal(obs.numpy(), np_(a_env.board.array).astype(np.uint8))
+    finally:
+        hs.close()
+
+
 def test_host_stepper_replay_chunks(E):
     """HostStepper over a replay-mode env: every chunk addresses its own slice of the per-board MT19937 streams, tile
     tables and stream positions (two-kernel replay step per chunk); a twin env stepped in one piece must agree."""
